@@ -1,0 +1,816 @@
+// libbagpu: C ABI (include/bagpu.h) + host driver of the Levenberg-Marquardt loop.
+//
+// The LM control flow restates OptimizationAlgorithmLevenberg::solve and SparseOptimizer::optimize
+// (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-169, sparse_optimizer.cpp:354-419):
+// decisions (rho, lambda, nu, the _nBad rule, the stop flag) are taken on the host in FP64 from sums the device
+// reduced in a fixed order; all per-edge / per-landmark / per-camera work is in the kernels.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bagpu.h"
+#include "ba_kernels.cuh"
+#include "chol.cuh"
+#include "pose_opt.cuh"
+
+namespace {
+
+struct DevBuf {                       // grow-only device buffer (the context's arena is a set of these)
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {                       // grow-only pinned host buffer
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+NcclApi g_nccl;
+
+enum { EV_BUILD = 0, EV_LINSOLVE = 1, EV_UPDATE = 2, EV_KINDS = 3 };
+
+}  // namespace
+
+struct bagpu_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    // ---- communicator (multi-GPU global BA)
+    ncclComm_t comm = nullptr; int world = 1, rank = 0;
+    // ---- BA problem state
+    bool have_problem = false;
+    int n_poses = 0, n_points = 0, n_free = 0, n_cams = 0, n_rigs = 0;
+    int64_t n_obs = 0;
+    bool identity_perm = true;
+    DevBuf d_lm_ptr, d_o_pose, d_o_point, d_o_meta, d_o_u, d_o_v, d_o_ur, d_o_w, d_cams, d_rigs, d_hidx, d_perm;
+    DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
+    DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b;
+    DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
+    DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
+    PinBuf h_status, h_stage;
+    std::vector<int> h_hidx;
+    double *pose_cur = nullptr, *pose_trial = nullptr, *pt_cur = nullptr, *pt_trial = nullptr;
+    int n_sys = 0, ld = 0;
+    int build_grid = 0;
+    // ---- pose batch state
+    bool have_pose = false;
+    int pb_frames = 0; int64_t pb_obs = 0;
+    DevBuf p_pose0, p_ptr, p_cams, p_rigs, p_xw, p_meta, p_u, p_v, p_ur, p_w, p_chi2, p_out, p_pose_out, p_ninl, p_fchi;
+    double pb_delta_mono = 0, pb_delta_stereo = 0; float pb_gate_mono = 0, pb_gate_stereo = 0;
+    // ---- timing
+    bagpu_timing tm;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    struct Pending { cudaEvent_t a, b; int kind; };
+    std::vector<Pending> pending;
+    cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(bagpu_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return fail(ctx, BAGPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define CKN(call)                                                                                         \
+    do {                                                                                                  \
+        ncclResult_t r__ = (call);                                                                        \
+        if (r__ != ncclSuccess) return fail(ctx, BAGPU_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
+    } while (0)
+
+void normalize_qt(const double *in, double *out) {      // SE3Quat(q,t) ctor: flip w<0, normalise (se3quat.h:62-64,280-285)
+    double x = in[3], y = in[4], z = in[5], w = in[6];
+    if (w < 0) { x *= -1; y *= -1; z *= -1; w *= -1; }
+    const double n = std::sqrt(x * x + y * y + z * z + w * w);
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+    out[3] = x / n; out[4] = y / n; out[5] = z / n; out[6] = w / n;
+}
+
+cudaEvent_t get_event(bagpu_ctx *ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+struct ScopedEv {
+    bagpu_ctx *c; cudaEvent_t a, b; int kind;
+    ScopedEv(bagpu_ctx *ctx, int k) : c(ctx), kind(k) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    ~ScopedEv() { cudaEventRecord(b, c->stream); c->pending.push_back({a, b, kind}); }
+};
+void resolve_events(bagpu_ctx *ctx) {      // call after a stream sync
+    for (auto &p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.kind == EV_BUILD) { ctx->tm.build_ms += ms; ctx->tm.build_launches++; }
+            else if (p.kind == EV_LINSOLVE) { ctx->tm.linsolve_ms += ms; ctx->tm.linsolve_launches++; }
+            else { ctx->tm.update_ms += ms; ctx->tm.update_launches++; }
+        }
+    }
+    ctx->pending.clear();
+    ctx->ev_used = 0;
+}
+
+// compose the observation meta word on the device from the caller's raw arrays
+__global__ void compose_meta_kernel(int64_t n, const uint8_t *kind, const int16_t *cam, const int16_t *rig, const uint8_t *flags, uint32_t *meta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = (rig[i] < 0) ? 255u : (uint32_t)rig[i];
+    meta[i] = (uint32_t)kind[i] | ((uint32_t)cam[i] << 2) | (r << 10) | ((flags[i] & BAGPU_FLAG_ROBUST) ? META_ROBUST : 0u);
+}
+template <typename T>
+__global__ void gather_perm_kernel(int64_t n, const int *__restrict__ perm, const T *__restrict__ in, T *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+__global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, float *o) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = baf_atan2f(y[i], x[i]);
+}
+
+inline int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+BaDev make_dev(bagpu_ctx *ctx, double delta_mono, double delta_stereo) {
+    BaDev D;
+    D.n_points = ctx->n_points; D.n_poses = ctx->n_poses; D.n_free = ctx->n_free; D.n_obs = ctx->n_obs;
+    D.lm_ptr = ctx->d_lm_ptr.as<int>(); D.o_pose = ctx->d_o_pose.as<int>(); D.o_point = ctx->d_o_point.as<int>();
+    D.o_meta = ctx->d_o_meta.as<uint32_t>();
+    D.o_u = ctx->d_o_u.as<double>(); D.o_v = ctx->d_o_v.as<double>(); D.o_ur = ctx->d_o_ur.as<double>(); D.o_w = ctx->d_o_w.as<double>();
+    D.cams = ctx->d_cams.as<bagpu_camera>(); D.rigs = ctx->d_rigs.as<double>(); D.pose_hidx = ctx->d_hidx.as<int>();
+    D.delta_mono = delta_mono; D.delta_stereo = delta_stereo;
+    return D;
+}
+
+int validate_problem(bagpu_ctx *ctx, const bagpu_problem *p) {
+    if (!p) return fail(ctx, BAGPU_ERR_ARG, "problem is NULL");
+    if (p->n_poses <= 0 || p->n_points <= 0 || p->n_obs <= 0 || p->n_cameras <= 0) return fail(ctx, BAGPU_ERR_ARG, "empty problem (poses %d points %d obs %lld cameras %d)", p->n_poses, p->n_points, (long long)p->n_obs, p->n_cameras);
+    if (p->n_obs >= (int64_t)INT32_MAX) return fail(ctx, BAGPU_ERR_ARG, "n_obs too large for one device shard");
+    if (!p->pose_qt || !p->pose_fixed || !p->points || !p->cameras || !p->obs_pose || !p->obs_point || !p->obs_cam || !p->obs_rig ||
+        !p->obs_kind || !p->obs_flags || !p->obs_u || !p->obs_v || !p->obs_inv_sigma2)
+        return fail(ctx, BAGPU_ERR_ARG, "NULL array in problem");
+    if (p->n_cameras > 255 || p->n_rigs > 254) return fail(ctx, BAGPU_ERR_ARG, "too many cameras/rigs");
+    bool any_stereo = false;
+    for (int64_t e = 0; e < p->n_obs; e++) {
+        if (p->obs_pose[e] < 0 || p->obs_pose[e] >= p->n_poses || p->obs_point[e] < 0 || p->obs_point[e] >= p->n_points)
+            return fail(ctx, BAGPU_ERR_ARG, "observation %lld: vertex index out of range", (long long)e);
+        if (p->obs_cam[e] < 0 || p->obs_cam[e] >= p->n_cameras) return fail(ctx, BAGPU_ERR_ARG, "observation %lld: camera index out of range", (long long)e);
+        const int k = p->obs_kind[e];
+        if (k > 2) return fail(ctx, BAGPU_ERR_ARG, "observation %lld: bad kind", (long long)e);
+        if (k == BAGPU_EDGE_BODY && (p->obs_rig[e] < 0 || p->obs_rig[e] >= p->n_rigs)) return fail(ctx, BAGPU_ERR_ARG, "observation %lld: rig index out of range", (long long)e);
+        if (k == BAGPU_EDGE_STEREO) any_stereo = true;
+    }
+    if (any_stereo && !p->obs_ur) return fail(ctx, BAGPU_ERR_ARG, "stereo edges need obs_ur");
+    return BAGPU_OK;
+}
+
+}  // namespace
+
+// ======================================================================================= API
+extern "C" {
+
+const char *bagpu_strerror(int code) {
+    switch (code) {
+        case BAGPU_OK: return "ok";
+        case BAGPU_TERMINATE_TRIALS: return "LM terminated: 10 failed trials or rho == 0";
+        case BAGPU_TERMINATE_NBAD: return "LM terminated: relative chi2 decrease < 1e-3 for 3 iterations";
+        case BAGPU_STOPPED: return "stopped by the caller's flag";
+        case BAGPU_ERR_CUDA: return "CUDA error";
+        case BAGPU_ERR_ARG: return "bad argument";
+        case BAGPU_ERR_NCCL: return "NCCL error";
+        case BAGPU_ERR_NO_DEVICE: return "no CUDA device";
+        case BAGPU_ERR_ALLOC: return "allocation failed";
+        default: return "unknown status";
+    }
+}
+const char *bagpu_last_error(const bagpu_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+int bagpu_init(int device_id, bagpu_ctx **out) {
+    if (!out) return BAGPU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return BAGPU_ERR_NO_DEVICE;   // no CPU fallback, by design
+    bagpu_ctx *ctx = new (std::nothrow) bagpu_ctx();
+    if (!ctx) return BAGPU_ERR_ALLOC;
+    if (device_id < 0) { if (cudaGetDevice(&device_id) != cudaSuccess) device_id = 0; }
+    if (device_id >= ndev) { delete ctx; return BAGPU_ERR_NO_DEVICE; }
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return BAGPU_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAGPU_ERR_CUDA; }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev_phase[i]);
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    *out = ctx;
+    return BAGPU_OK;
+}
+
+void bagpu_destroy(bagpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
+                      &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_sys, &ctx->d_xp,
+                      &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
+                      &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
+                      &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
+    for (DevBuf *b : bufs) b->release();
+    ctx->h_status.release(); ctx->h_stage.release();
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 4; i++) if (ctx->ev_phase[i]) cudaEventDestroy(ctx->ev_phase[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int bagpu_comm_unique_id(uint8_t id_out[128]) {
+    if (!g_nccl.load()) return BAGPU_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return BAGPU_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id_out, &id, 128);
+    return BAGPU_OK;
+}
+
+int bagpu_comm_init(bagpu_ctx *ctx, int world_size, int rank, const uint8_t id[128]) {
+    if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) return fail(ctx, BAGPU_ERR_ARG, "bad communicator arguments");
+    if (world_size == 1) { ctx->world = 1; ctx->rank = 0; return BAGPU_OK; }
+    if (!g_nccl.load()) return fail(ctx, BAGPU_ERR_NCCL, "cannot dlopen libnccl.so.2");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    CKN(g_nccl.CommInitRank(&ctx->comm, world_size, uid, rank));
+    ctx->world = world_size; ctx->rank = rank;
+    return BAGPU_OK;
+}
+
+int bagpu_pin_host(void *p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? BAGPU_OK : BAGPU_ERR_CUDA; }
+int bagpu_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? BAGPU_OK : BAGPU_ERR_CUDA; }
+
+// ------------------------------------------------------------------------------- upload
+int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
+    if (!ctx) return BAGPU_ERR_ARG;
+    int rc = validate_problem(ctx, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_phase[0], st));
+    ctx->have_problem = false;
+    const int Nt = p->n_poses, Np = p->n_points;
+    const int64_t Ne = p->n_obs;
+    ctx->n_poses = Nt; ctx->n_points = Np; ctx->n_obs = Ne; ctx->n_cams = p->n_cameras; ctx->n_rigs = p->n_rigs;
+    int64_t h2d = 0;
+
+    // --- order: landmark-major, pose-ascending inside a landmark, insertion order preserved among equals
+    bool sorted = true;
+    for (int64_t e = 1; e < Ne; e++) {
+        const int a = p->obs_point[e - 1], b = p->obs_point[e];
+        if (a > b || (a == b && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted = false; break; }
+    }
+    std::vector<int> lm_ptr((size_t)Np + 1, 0);
+    for (int64_t e = 0; e < Ne; e++) lm_ptr[(size_t)p->obs_point[e] + 1]++;
+    for (int j = 0; j < Np; j++) lm_ptr[j + 1] += lm_ptr[j];
+    std::vector<int> perm;
+    if (!sorted) {
+        perm.resize(Ne);
+        std::vector<int> cursor(lm_ptr.begin(), lm_ptr.end() - 1);
+        for (int64_t e = 0; e < Ne; e++) perm[cursor[p->obs_point[e]]++] = (int)e;       // stable counting sort by point
+        for (int j = 0; j < Np; j++)                                                        // stable insertion sort by pose
+            for (int a = lm_ptr[j] + 1; a < lm_ptr[j + 1]; a++) {
+                const int v = perm[a]; int b = a - 1;
+                while (b >= lm_ptr[j] && p->obs_pose[perm[b]] > p->obs_pose[v]) { perm[b + 1] = perm[b]; b--; }
+                perm[b + 1] = v;
+            }
+    }
+    ctx->identity_perm = sorted;
+
+    // --- poses / free index
+    CK(ctx->h_stage.ensure(sizeof(double) * 7 * (size_t)Nt + sizeof(double) * 7 * (size_t)std::max(1, p->n_rigs)));
+    double *hp = ctx->h_stage.as<double>();
+    for (int i = 0; i < Nt; i++) normalize_qt(p->pose_qt + 7 * (size_t)i, hp + 7 * (size_t)i);
+    double *hr = hp + 7 * (size_t)Nt;
+    for (int i = 0; i < p->n_rigs; i++) normalize_qt(p->rigs[i].qt, hr + 7 * (size_t)i);
+    ctx->h_hidx.assign(Nt, -1);
+    int nf = 0;
+    for (int i = 0; i < Nt; i++) if (!p->pose_fixed[i]) ctx->h_hidx[i] = nf++;
+    ctx->n_free = nf;
+
+    CK(ctx->d_pose_a.ensure(sizeof(double) * 7 * (size_t)Nt)); CK(ctx->d_pose_b.ensure(sizeof(double) * 7 * (size_t)Nt));
+    CK(ctx->d_pose_init.ensure(sizeof(double) * 7 * (size_t)Nt));
+    CK(ctx->d_pt_a.ensure(sizeof(double) * 3 * (size_t)Np)); CK(ctx->d_pt_b.ensure(sizeof(double) * 3 * (size_t)Np));
+    CK(ctx->d_hidx.ensure(sizeof(int) * (size_t)Nt));
+    CK(ctx->d_cams.ensure(sizeof(bagpu_camera) * (size_t)p->n_cameras));
+    CK(ctx->d_rigs.ensure(sizeof(double) * 7 * (size_t)std::max(1, p->n_rigs)));
+    CK(ctx->d_lm_ptr.ensure(sizeof(int) * ((size_t)Np + 1)));
+    CK(cudaMemcpyAsync(ctx->d_pose_a.p, hp, sizeof(double) * 7 * (size_t)Nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_pose_init.p, ctx->d_pose_a.p, sizeof(double) * 7 * (size_t)Nt, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_pose_b.p, ctx->d_pose_a.p, sizeof(double) * 7 * (size_t)Nt, cudaMemcpyDeviceToDevice, st));
+    if (p->n_rigs) CK(cudaMemcpyAsync(ctx->d_rigs.p, hr, sizeof(double) * 7 * (size_t)p->n_rigs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_pt_a.p, p->points, sizeof(double) * 3 * (size_t)Np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_hidx.p, ctx->h_hidx.data(), sizeof(int) * (size_t)Nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_cams.p, p->cameras, sizeof(bagpu_camera) * (size_t)p->n_cameras, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_lm_ptr.p, lm_ptr.data(), sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
+    h2d += sizeof(double) * (7 * (int64_t)Nt + 3 * (int64_t)Np) + sizeof(int) * ((int64_t)Nt + Np + 1);
+
+    // --- observations: raw arrays go up as they are; permutation and meta packing happen on the device
+    const size_t ne = (size_t)Ne;
+    CK(ctx->d_o_pose.ensure(4 * ne)); CK(ctx->d_o_point.ensure(4 * ne)); CK(ctx->d_o_meta.ensure(4 * ne));
+    CK(ctx->d_o_u.ensure(8 * ne)); CK(ctx->d_o_v.ensure(8 * ne)); CK(ctx->d_o_w.ensure(8 * ne)); CK(ctx->d_o_ur.ensure(8 * ne));
+    CK(ctx->d_raw8a.ensure(ne)); CK(ctx->d_raw8b.ensure(ne)); CK(ctx->d_raw16a.ensure(2 * ne)); CK(ctx->d_raw16b.ensure(2 * ne));
+    CK(ctx->d_chi2.ensure(8 * ne)); CK(ctx->d_depth.ensure(ne));
+    CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * ne, st));
+    const int g = grid_for(Ne, 256);
+    CK(cudaMemcpyAsync(ctx->d_raw8a.p, p->obs_kind, ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw8b.p, p->obs_flags, ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw16a.p, p->obs_cam, 2 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw16b.p, p->obs_rig, 2 * ne, cudaMemcpyHostToDevice, st));
+    h2d += 6 * Ne;
+    if (sorted) {
+        CK(cudaMemcpyAsync(ctx->d_o_pose.p, p->obs_pose, 4 * ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_o_point.p, p->obs_point, 4 * ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_o_u.p, p->obs_u, 8 * ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_o_v.p, p->obs_v, 8 * ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_o_w.p, p->obs_inv_sigma2, 8 * ne, cudaMemcpyHostToDevice, st));
+        if (p->obs_ur) CK(cudaMemcpyAsync(ctx->d_o_ur.p, p->obs_ur, 8 * ne, cudaMemcpyHostToDevice, st));
+        compose_meta_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_raw8a.as<uint8_t>(), ctx->d_raw16a.as<int16_t>(), ctx->d_raw16b.as<int16_t>(),
+                                               ctx->d_raw8b.as<uint8_t>(), ctx->d_o_meta.as<uint32_t>());
+    } else {
+        CK(ctx->d_perm.ensure(4 * ne)); CK(ctx->d_rawd.ensure(8 * ne));
+        CK(cudaMemcpyAsync(ctx->d_perm.p, perm.data(), 4 * ne, cudaMemcpyHostToDevice, st));
+        h2d += 4 * Ne;
+        // meta in caller order first (into d_rawd as scratch), then gather everything through perm
+        uint32_t *meta_raw = ctx->d_rawd.as<uint32_t>();
+        compose_meta_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_raw8a.as<uint8_t>(), ctx->d_raw16a.as<int16_t>(), ctx->d_raw16b.as<int16_t>(),
+                                               ctx->d_raw8b.as<uint8_t>(), meta_raw);
+        gather_perm_kernel<uint32_t><<<g, 256, 0, st>>>(Ne, ctx->d_perm.as<int>(), meta_raw, ctx->d_o_meta.as<uint32_t>());
+        struct { const void *src; void *dst; int w; } cols[] = {
+            {p->obs_pose, ctx->d_o_pose.p, 4}, {p->obs_point, ctx->d_o_point.p, 4}, {p->obs_u, ctx->d_o_u.p, 8},
+            {p->obs_v, ctx->d_o_v.p, 8}, {p->obs_inv_sigma2, ctx->d_o_w.p, 8}, {p->obs_ur, ctx->d_o_ur.p, 8}};
+        for (auto &c : cols) {
+            if (!c.src) continue;
+            CK(cudaMemcpyAsync(ctx->d_rawd.p, c.src, (size_t)c.w * ne, cudaMemcpyHostToDevice, st));
+            if (c.w == 4) gather_perm_kernel<int><<<g, 256, 0, st>>>(Ne, ctx->d_perm.as<int>(), ctx->d_rawd.as<int>(), (int *)c.dst);
+            else gather_perm_kernel<double><<<g, 256, 0, st>>>(Ne, ctx->d_perm.as<int>(), ctx->d_rawd.as<double>(), (double *)c.dst);
+        }
+    }
+    h2d += (4 + 4 + 8 + 8 + 8 + (p->obs_ur ? 8 : 0)) * Ne;
+    CK(cudaGetLastError());
+
+    // --- reduced camera system buffers
+    const int n = 6 * nf;
+    ctx->n_sys = n; ctx->ld = (n + 1 + 3) & ~3;
+    CK(ctx->d_sys.ensure(sizeof(double) * ((size_t)std::max(1, n) * ctx->ld + 3 * (size_t)std::max(1, n))));
+    CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
+    ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
+    CK(ctx->d_parts.ensure(sizeof(double) * 4 * (size_t)ctx->build_grid));
+    CK(ctx->d_status.ensure(sizeof(double) * 16));
+    CK(ctx->d_fail.ensure(sizeof(int) * 4));
+    CK(ctx->d_count.ensure(sizeof(unsigned long long) * 2));
+    CK(ctx->h_status.ensure(sizeof(double) * 32));
+    ctx->pose_cur = ctx->d_pose_a.as<double>(); ctx->pose_trial = ctx->d_pose_b.as<double>();
+    ctx->pt_cur = ctx->d_pt_a.as<double>(); ctx->pt_trial = ctx->d_pt_b.as<double>();
+    CK(cudaEventRecord(ctx->ev_phase[1], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
+    ctx->tm.h2d_ms = ms; ctx->tm.h2d_bytes = h2d;
+    ctx->have_problem = true;
+    return BAGPU_OK;
+}
+
+// ------------------------------------------------------------------------------- solve
+namespace {
+
+int all_reduce_sum(bagpu_ctx *ctx, double *buf, size_t count) {
+    if (ctx->world <= 1) return BAGPU_OK;
+    CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    return BAGPU_OK;
+}
+int all_reduce_max(bagpu_ctx *ctx, double *buf, size_t count) {
+    if (ctx->world <= 1) return BAGPU_OK;
+    CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
+    return BAGPU_OK;
+}
+
+// read `count` doubles of the device status record (one stream sync)
+int read_status(bagpu_ctx *ctx, double *out, int count) {
+    CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_status.p, sizeof(double) * count);
+    resolve_events(ctx);
+    return BAGPU_OK;
+}
+
+int launch_chol(bagpu_ctx *ctx, CholArgs &a) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_solve_kernel, CH_THREADS, 0));
+    if (occ < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
+    const int nt = (a.n + 1 + CH_TB - 1) / CH_TB;
+    const int want = std::max(1, nt * (nt + 1) / 2);
+    const int grid = std::max(1, std::min(ctx->n_sm * std::min(occ, 2), want));
+    void *args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, 0, ctx->stream));
+    return BAGPU_OK;
+}
+
+int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
+    cudaStream_t st = ctx->stream;
+    BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
+    const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid;
+    double *S = ctx->d_sys.as<double>();
+    double *bp = S + (size_t)std::max(1, n) * ld, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
+    double *parts = ctx->d_parts.as<double>();
+    double *part_chi_b = parts, *part_max = parts + G, *part_chi_u = parts + 2 * G, *part_scale = parts + 3 * G;
+    double *dstat = ctx->d_status.as<double>();
+    auto stop = [&]() { return s->stop_flag && *s->stop_flag; };
+
+    int status = BAGPU_OK;
+    double lambda = -1, ni = 2; int nBad = 0;
+    bool ok = true;
+    for (int it = 0; it < iterations && !stop() && ok; it++) {
+        double currentChi = 0, iniChi = 0;
+        if (it == 0) {
+            // computeLambdaInit: tau * max diagonal of Hpp and Hll (optimization_algorithm_levenberg.cpp:171-185)
+            CK(cudaMemsetAsync(hpp, 0, sizeof(double) * std::max(1, n), st));
+            BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max;
+            { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
+            ctx->tm.total_launches++;
+            int rc = all_reduce_sum(ctx, hpp, std::max(1, n)); if (rc) return rc;
+            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_chi_b, nullptr, part_max, nullptr, hpp, n, dstat);
+            ctx->tm.total_launches++;
+            if (ctx->world > 1) { rc = all_reduce_sum(ctx, dstat, 1); if (rc) return rc; rc = all_reduce_max(ctx, dstat + 2, 1); if (rc) return rc; }
+            double h[3];
+            rc = read_status(ctx, h, 3); if (rc) return rc;
+            lambda = (s->lambda_init > 0) ? s->lambda_init : 1e-5 * h[2];
+            ni = 2; nBad = 0;
+            ctx->tm.edge_linearisations += n_active;
+        }
+        double rho = 0; int qmax = 0;
+        bool first = true;
+        do {
+            // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
+            CK(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)std::max(1, n) * ld + 2 * (size_t)std::max(1, n)), st));
+            CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
+            BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max;
+            { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
+            ctx->tm.total_launches++;
+            ctx->tm.edge_linearisations += n_active;
+            int rc = all_reduce_sum(ctx, S, (size_t)std::max(1, n) * ld + 2 * (size_t)std::max(1, n)); if (rc) return rc;
+            if (n > 0) {
+                CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
+                ca.x = ctx->d_xp.as<double>(); ca.fail = ctx->d_fail.as<int>();
+                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca); if (rc) return rc; }
+                ctx->tm.total_launches++;
+            }
+            pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
+                                                  ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
+            UpdateOut U; U.lambda = lambda; U.xp = ctx->d_xp.as<double>(); U.pose_trial = ctx->pose_trial; U.pt_trial = ctx->pt_trial;
+            U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale;
+            { ScopedEv ev(ctx, EV_UPDATE); update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U); }
+            ctx->tm.total_launches += 2;
+            ctx->tm.edge_linearisations += 0; ctx->tm.edge_evaluations += n_active;
+            // dstat[0]=chi2 at the linearisation point, [1]=trial chi2, [2]=landmark part of scale, [4]=pose part of scale
+            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_chi_b, part_chi_u, nullptr, nullptr, nullptr, 0, dstat);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8);
+            ctx->tm.total_launches += 2;
+            CK(cudaMemcpyAsync(dstat + 2, dstat + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(dstat + 5, ctx->d_fail.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            rc = all_reduce_sum(ctx, dstat, 3); if (rc) return rc;
+            CK(cudaGetLastError());
+            double h[6];
+            rc = read_status(ctx, h, 6); if (rc) return rc;
+            int failflag; memcpy(&failflag, &h[5], sizeof(int));
+            const bool ok2 = (failflag == 0);
+            if (first) { currentChi = h[0]; iniChi = currentChi; first = false; }
+            double tempChi = ok2 ? h[1] : DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = h[2] + h[4];
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                const double scaleFactor = std::max(1. / 3., alpha);
+                lambda *= scaleFactor;
+                ni = 2;
+                currentChi = tempChi;
+                std::swap(ctx->pose_cur, ctx->pose_trial);          // discardTop(): the trial state becomes current
+                std::swap(ctx->pt_cur, ctx->pt_trial);
+            } else {
+                lambda *= ni;
+                ni *= 2;                                            // pop(): keep the current state; edge chi2 stay as evaluated
+            }
+            qmax++; ctx->tm.lm_trials++;
+        } while (rho < 0 && qmax < 10 && !stop());
+        ctx->tm.lm_iterations++;
+        int stt = BAGPU_OK;
+        if (qmax == 10 || rho == 0) stt = BAGPU_TERMINATE_TRIALS;
+        else {
+            if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+            if (nBad >= 3) stt = BAGPU_TERMINATE_NBAD;
+        }
+        if (res && res->trace && res->n_trace < s->max_trace) {
+            bagpu_trace &t = res->trace[res->n_trace++];
+            t.round = round; t.iteration = it; t.chi2_before = iniChi; t.chi2_after = currentChi; t.lambda = lambda; t.trials = qmax; t.status = stt;
+        }
+        status = stt;
+        ok = (stt == BAGPU_OK);
+    }
+    if (stop() && status == BAGPU_OK) status = BAGPU_STOPPED;
+    *status_out = status;
+    return BAGPU_OK;
+}
+
+}  // namespace
+
+int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *r) {
+    if (!ctx || !s || !s->rounds || s->n_rounds < 1) return fail(ctx, BAGPU_ERR_ARG, "bad schedule");
+    if (!ctx->have_problem) return fail(ctx, BAGPU_ERR_ARG, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->ev_used = 0; ctx->pending.clear();
+    ctx->tm.build_ms = ctx->tm.linsolve_ms = ctx->tm.update_ms = 0;
+    ctx->tm.build_launches = ctx->tm.update_launches = ctx->tm.linsolve_launches = ctx->tm.total_launches = 0;
+    ctx->tm.lm_iterations = ctx->tm.lm_trials = ctx->tm.edge_linearisations = ctx->tm.edge_evaluations = 0;
+    ctx->tm.pcg_iterations = 0; ctx->tm.schur_blocks = ctx->n_free * (ctx->n_free + 1) / 2;
+    CK(cudaEventRecord(ctx->ev_phase[0], st));
+    if (r) { r->n_trace = 0; r->status = BAGPU_OK; }
+    BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
+    const int g = grid_for(ctx->n_obs, 256);
+    int status = BAGPU_OK;
+    auto stop = [&]() { return s->stop_flag && *s->stop_flag; };
+    for (int k = 0; k < s->n_rounds; k++) {
+        const bagpu_round &rd = s->rounds[k];
+        if (rd.reset_pose) CK(cudaMemcpyAsync(ctx->pose_cur, ctx->d_pose_init.p, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToDevice, st));
+        if (stop()) { status = BAGPU_STOPPED; break; }
+        // initializeOptimization(0): active edges = level 0 (sparse_optimizer.cpp:199-267)
+        CK(cudaMemsetAsync(ctx->d_count.p, 0, sizeof(unsigned long long), st));
+        count_active_kernel<<<g, 256, 0, st>>>(D.o_meta, ctx->n_obs, ctx->d_count.as<unsigned long long>());
+        unsigned long long n_active = 0;
+        CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(&n_active, ctx->h_status.p, sizeof(n_active));
+        bool any_active = n_active > 0;
+        if (ctx->world > 1) {       // every rank must take the same branch
+            double *ds = ctx->d_status.as<double>();
+            double v = (double)n_active;
+            CK(cudaMemcpyAsync(ds + 12, &v, sizeof(double), cudaMemcpyHostToDevice, st));
+            int rc = all_reduce_sum(ctx, ds + 12, 1); if (rc) return rc;
+            CK(cudaMemcpyAsync(&v, ds + 12, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            any_active = v > 0.5;
+        }
+        if (any_active) {
+            int rc = optimize(ctx, s, k, rd.iterations, (int64_t)n_active, r, &status);
+            if (rc) return rc;
+        }
+        if (rd.gate_after != BAGPU_GATE_NONE || rd.drop_kernel_after) {
+            if (rd.gate_after == BAGPU_GATE_LBA && stop()) { status = BAGPU_STOPPED; break; }
+            gate_kernel<<<g, 256, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, ctx->d_chi2.as<double>(), nullptr, rd.gate_after,
+                                           rd.gate_mono, rd.gate_stereo, rd.drop_kernel_after);
+            ctx->tm.total_launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_phase[1], st));
+    CK(cudaStreamSynchronize(st));
+    resolve_events(ctx);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
+    ctx->tm.solve_ms = ms;
+    if (r) {
+        r->status = status;
+        int rc = bagpu_download(ctx, r);
+        if (rc) return rc;
+    }
+    return status;
+}
+
+int bagpu_download(bagpu_ctx *ctx, bagpu_result *r) {
+    if (!ctx || !r) return BAGPU_ERR_ARG;
+    if (!ctx->have_problem) return fail(ctx, BAGPU_ERR_ARG, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_phase[2], st));
+    const size_t ne = (size_t)ctx->n_obs;
+    const int g = grid_for(ctx->n_obs, 256);
+    BaDev D = make_dev(ctx, 0, 0);
+    int64_t d2h = 0;
+    // isDepthPositive on the final estimates, in sorted order
+    gate_kernel<<<g, 256, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, ctx->d_chi2.as<double>(), ctx->d_depth.as<uint8_t>(), BAGPU_GATE_NONE, 0, 0, 0);
+    const double *chi_src = ctx->d_chi2.as<double>();
+    const uint8_t *dp_src = ctx->d_depth.as<uint8_t>();
+    CK(ctx->d_out_u8b.ensure(ne));
+    uint8_t *lvl_src = ctx->d_out_u8b.as<uint8_t>();
+    if (!ctx->identity_perm) {
+        CK(ctx->d_out_chi2.ensure(8 * ne)); CK(ctx->d_out_u8a.ensure(ne));
+        scatter_perm_kernel<double><<<g, 256, 0, st>>>(ctx->n_obs, ctx->d_perm.as<int>(), ctx->d_chi2.as<double>(), ctx->d_out_chi2.as<double>());
+        scatter_perm_kernel<uint8_t><<<g, 256, 0, st>>>(ctx->n_obs, ctx->d_perm.as<int>(), ctx->d_depth.as<uint8_t>(), ctx->d_out_u8a.as<uint8_t>());
+        level_from_meta_kernel<<<g, 256, 0, st>>>(ctx->n_obs, ctx->d_perm.as<int>(), D.o_meta, lvl_src);
+        chi_src = ctx->d_out_chi2.as<double>(); dp_src = ctx->d_out_u8a.as<uint8_t>();
+    } else {
+        level_from_meta_kernel<<<g, 256, 0, st>>>(ctx->n_obs, nullptr, D.o_meta, lvl_src);
+    }
+    if (r->pose_qt) { CK(cudaMemcpyAsync(r->pose_qt, ctx->pose_cur, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToHost, st)); d2h += 56 * (int64_t)ctx->n_poses; }
+    if (r->points) { CK(cudaMemcpyAsync(r->points, ctx->pt_cur, sizeof(double) * 3 * (size_t)ctx->n_points, cudaMemcpyDeviceToHost, st)); d2h += 24 * (int64_t)ctx->n_points; }
+    if (r->edge_chi2) { CK(cudaMemcpyAsync(r->edge_chi2, chi_src, 8 * ne, cudaMemcpyDeviceToHost, st)); d2h += 8 * (int64_t)ne; }
+    if (r->edge_depth_pos) { CK(cudaMemcpyAsync(r->edge_depth_pos, dp_src, ne, cudaMemcpyDeviceToHost, st)); d2h += (int64_t)ne; }
+    if (r->edge_level) { CK(cudaMemcpyAsync(r->edge_level, lvl_src, ne, cudaMemcpyDeviceToHost, st)); d2h += (int64_t)ne; }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_phase[3], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_phase[2], ctx->ev_phase[3]);
+    ctx->tm.d2h_ms = ms; ctx->tm.d2h_bytes = d2h;
+    return BAGPU_OK;
+}
+
+int bagpu_solve_ba(bagpu_ctx *ctx, const bagpu_problem *p, const bagpu_schedule *s, bagpu_result *r) {
+    int rc = bagpu_upload(ctx, p);
+    if (rc) return rc;
+    return bagpu_solve_resident(ctx, s, r);
+}
+
+// ------------------------------------------------------------------------------- pose batch
+int bagpu_pose_upload(bagpu_ctx *ctx, const bagpu_pose_batch *b) {
+    if (!ctx || !b) return BAGPU_ERR_ARG;
+    if (b->n_frames <= 0 || !b->pose_qt || !b->frame_ptr || !b->cameras || b->n_cameras <= 0 || b->n_cameras > 255 || b->n_rigs > 254)
+        return fail(ctx, BAGPU_ERR_ARG, "bad pose batch");
+    const int F = b->n_frames; const int64_t Ne = b->n_obs;
+    if (b->frame_ptr[0] != 0 || b->frame_ptr[F] != Ne) return fail(ctx, BAGPU_ERR_ARG, "frame_ptr does not cover the edges");
+    if (Ne > 0 && (!b->xw || !b->obs_cam || !b->obs_rig || !b->obs_kind || !b->obs_u || !b->obs_v || !b->obs_inv_sigma2)) return fail(ctx, BAGPU_ERR_ARG, "NULL array in pose batch");
+    bool any_stereo = false;
+    for (int64_t e = 0; e < Ne; e++) {
+        if (b->obs_cam[e] < 0 || b->obs_cam[e] >= b->n_cameras || b->obs_kind[e] > 2) return fail(ctx, BAGPU_ERR_ARG, "edge %lld: bad camera/kind", (long long)e);
+        if (b->obs_kind[e] == BAGPU_EDGE_BODY && (b->obs_rig[e] < 0 || b->obs_rig[e] >= b->n_rigs)) return fail(ctx, BAGPU_ERR_ARG, "edge %lld: bad rig", (long long)e);
+        if (b->obs_kind[e] == BAGPU_EDGE_STEREO) any_stereo = true;
+    }
+    if (any_stereo && !b->obs_ur) return fail(ctx, BAGPU_ERR_ARG, "stereo edges need obs_ur");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_phase[0], st));
+    ctx->have_pose = false;
+    const size_t ne = (size_t)std::max<int64_t>(1, Ne);
+    CK(ctx->h_stage.ensure(sizeof(double) * 7 * ((size_t)F + (size_t)std::max(1, b->n_rigs))));
+    double *hp = ctx->h_stage.as<double>();
+    for (int i = 0; i < F; i++) normalize_qt(b->pose_qt + 7 * (size_t)i, hp + 7 * (size_t)i);
+    double *hr = hp + 7 * (size_t)F;
+    for (int i = 0; i < b->n_rigs; i++) normalize_qt(b->rigs[i].qt, hr + 7 * (size_t)i);
+    CK(ctx->p_pose0.ensure(56 * (size_t)F)); CK(ctx->p_ptr.ensure(8 * ((size_t)F + 1))); CK(ctx->p_cams.ensure(sizeof(bagpu_camera) * (size_t)b->n_cameras));
+    CK(ctx->p_rigs.ensure(56 * (size_t)std::max(1, b->n_rigs))); CK(ctx->p_xw.ensure(24 * ne)); CK(ctx->p_meta.ensure(4 * ne));
+    CK(ctx->p_u.ensure(8 * ne)); CK(ctx->p_v.ensure(8 * ne)); CK(ctx->p_ur.ensure(8 * ne)); CK(ctx->p_w.ensure(8 * ne));
+    CK(ctx->p_chi2.ensure(8 * ne)); CK(ctx->p_out.ensure(ne)); CK(ctx->p_pose_out.ensure(56 * (size_t)F)); CK(ctx->p_ninl.ensure(4 * (size_t)F));
+    CK(ctx->p_fchi.ensure(8 * (size_t)F));
+    CK(ctx->d_raw8a.ensure(ne)); CK(ctx->d_raw8b.ensure(ne)); CK(ctx->d_raw16a.ensure(2 * ne)); CK(ctx->d_raw16b.ensure(2 * ne));
+    CK(cudaMemcpyAsync(ctx->p_pose0.p, hp, 56 * (size_t)F, cudaMemcpyHostToDevice, st));
+    if (b->n_rigs) CK(cudaMemcpyAsync(ctx->p_rigs.p, hr, 56 * (size_t)b->n_rigs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->p_ptr.p, b->frame_ptr, 8 * ((size_t)F + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->p_cams.p, b->cameras, sizeof(bagpu_camera) * (size_t)b->n_cameras, cudaMemcpyHostToDevice, st));
+    int64_t h2d = 56 * (int64_t)F + 8 * ((int64_t)F + 1);
+    if (Ne > 0) {
+        CK(cudaMemcpyAsync(ctx->p_xw.p, b->xw, 24 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->p_u.p, b->obs_u, 8 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->p_v.p, b->obs_v, 8 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        if (b->obs_ur) CK(cudaMemcpyAsync(ctx->p_ur.p, b->obs_ur, 8 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->p_w.p, b->obs_inv_sigma2, 8 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_raw8a.p, b->obs_kind, (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->d_raw8b.p, 0, (size_t)Ne, st));
+        CK(cudaMemcpyAsync(ctx->d_raw16a.p, b->obs_cam, 2 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_raw16b.p, b->obs_rig, 2 * (size_t)Ne, cudaMemcpyHostToDevice, st));
+        compose_meta_kernel<<<grid_for(Ne, 256), 256, 0, st>>>(Ne, ctx->d_raw8a.as<uint8_t>(), ctx->d_raw16a.as<int16_t>(), ctx->d_raw16b.as<int16_t>(),
+                                                             ctx->d_raw8b.as<uint8_t>(), ctx->p_meta.as<uint32_t>());
+        h2d += (24 + 8 * (b->obs_ur ? 4 : 3) + 5) * Ne;
+    }
+    CK(cudaGetLastError());
+    ctx->pb_frames = F; ctx->pb_obs = Ne;
+    ctx->pb_delta_mono = b->delta_mono; ctx->pb_delta_stereo = b->delta_stereo; ctx->pb_gate_mono = b->gate_mono; ctx->pb_gate_stereo = b->gate_stereo;
+    CK(cudaEventRecord(ctx->ev_phase[1], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
+    ctx->tm.h2d_ms = ms; ctx->tm.h2d_bytes = h2d;
+    ctx->have_pose = true;
+    return BAGPU_OK;
+}
+
+int bagpu_pose_solve_resident(bagpu_ctx *ctx, bagpu_pose_result *r) {
+    if (!ctx) return BAGPU_ERR_ARG;
+    if (!ctx->have_pose) return fail(ctx, BAGPU_ERR_ARG, "no pose batch uploaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PoseDev D;
+    D.n_frames = ctx->pb_frames; D.pose0 = ctx->p_pose0.as<double>(); D.frame_ptr = ctx->p_ptr.as<int64_t>();
+    D.cams = ctx->p_cams.as<bagpu_camera>(); D.rigs = ctx->p_rigs.as<double>(); D.xw = ctx->p_xw.as<double>();
+    D.o_meta = ctx->p_meta.as<uint32_t>(); D.o_u = ctx->p_u.as<double>(); D.o_v = ctx->p_v.as<double>(); D.o_ur = ctx->p_ur.as<double>();
+    D.o_w = ctx->p_w.as<double>(); D.delta_mono = ctx->pb_delta_mono; D.delta_stereo = ctx->pb_delta_stereo;
+    D.gate_mono = ctx->pb_gate_mono; D.gate_stereo = ctx->pb_gate_stereo; D.chi2 = ctx->p_chi2.as<double>();
+    D.outlier = ctx->p_out.as<uint8_t>(); D.pose_out = ctx->p_pose_out.as<double>(); D.n_inliers = ctx->p_ninl.as<int>();
+    D.final_chi2 = ctx->p_fchi.as<double>();
+    CK(cudaEventRecord(ctx->ev_phase[0], st));
+    pose_opt_kernel<<<ctx->pb_frames, PO_THREADS, 0, st>>>(D);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_phase[1], st));
+    int64_t d2h = 0;
+    if (r) {
+        CK(cudaEventRecord(ctx->ev_phase[2], st));
+        const size_t F = (size_t)ctx->pb_frames;
+        if (r->pose_qt) { CK(cudaMemcpyAsync(r->pose_qt, D.pose_out, 56 * F, cudaMemcpyDeviceToHost, st)); d2h += 56 * (int64_t)F; }
+        if (r->outlier && ctx->pb_obs) { CK(cudaMemcpyAsync(r->outlier, D.outlier, (size_t)ctx->pb_obs, cudaMemcpyDeviceToHost, st)); d2h += ctx->pb_obs; }
+        if (r->n_inliers) { CK(cudaMemcpyAsync(r->n_inliers, D.n_inliers, 4 * F, cudaMemcpyDeviceToHost, st)); d2h += 4 * (int64_t)F; }
+        if (r->final_chi2) { CK(cudaMemcpyAsync(r->final_chi2, D.final_chi2, 8 * F, cudaMemcpyDeviceToHost, st)); d2h += 8 * (int64_t)F; }
+        CK(cudaEventRecord(ctx->ev_phase[3], st));
+    }
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
+    ctx->tm.solve_ms = ms; ctx->tm.total_launches = 1;
+    if (r) { cudaEventElapsedTime(&ms, ctx->ev_phase[2], ctx->ev_phase[3]); ctx->tm.d2h_ms = ms; ctx->tm.d2h_bytes = d2h; }
+    return BAGPU_OK;
+}
+
+int bagpu_pose_opt_batch(bagpu_ctx *ctx, const bagpu_pose_batch *b, bagpu_pose_result *r) {
+    int rc = bagpu_pose_upload(ctx, b);
+    if (rc) return rc;
+    return bagpu_pose_solve_resident(ctx, r);
+}
+
+int bagpu_get_timing(const bagpu_ctx *ctx, bagpu_timing *out) {
+    if (!ctx || !out) return BAGPU_ERR_ARG;
+    *out = ctx->tm;
+    return BAGPU_OK;
+}
+
+int bagpu_test_atan2f(bagpu_ctx *ctx, const float *y, const float *x, float *out, int64_t n) {
+    if (!ctx || n <= 0) return BAGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf a, b, c;
+    CK(a.ensure(4 * (size_t)n)); CK(b.ensure(4 * (size_t)n)); CK(c.ensure(4 * (size_t)n));
+    CK(cudaMemcpyAsync(a.p, y, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b.p, x, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    atan2f_test_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, a.as<float>(), b.as<float>(), c.as<float>());
+    CK(cudaMemcpyAsync(out, c.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    a.release(); b.release(); c.release();
+    return BAGPU_OK;
+}
+
+}  // extern "C"
