@@ -220,6 +220,7 @@ int  bagpu_solve_ba(bagpu_ctx *ctx, const bagpu_problem *p, const bagpu_schedule
 int  bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p);
 int  bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *r /* may be NULL: no D2H */);
 int  bagpu_download(bagpu_ctx *ctx, bagpu_result *r);
+int  bagpu_reset_resident(bagpu_ctx *ctx);   /* estimates, edge levels and kernels back to the uploaded state */
 
 int  bagpu_pose_opt_batch(bagpu_ctx *ctx, const bagpu_pose_batch *b, bagpu_pose_result *r);
 /* Split form of the above for device-resident timing. */

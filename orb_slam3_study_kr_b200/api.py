@@ -28,7 +28,7 @@ _LIB = None
 
 EXPORTS = ["bagpu_init", "bagpu_destroy", "bagpu_strerror", "bagpu_last_error", "bagpu_comm_unique_id",
            "bagpu_comm_init", "bagpu_pin_host", "bagpu_unpin_host", "bagpu_solve_ba", "bagpu_upload",
-           "bagpu_solve_resident", "bagpu_download", "bagpu_pose_opt_batch", "bagpu_pose_upload",
+           "bagpu_solve_resident", "bagpu_download", "bagpu_reset_resident", "bagpu_pose_opt_batch", "bagpu_pose_upload",
            "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f"]
 
 
@@ -62,6 +62,7 @@ def load_library():
     L.bagpu_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.bagpu_solve_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bagpu_download.argtypes = [C.c_void_p, C.c_void_p]
+    L.bagpu_reset_resident.argtypes = [C.c_void_p]
     L.bagpu_pose_opt_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bagpu_pose_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.bagpu_pose_solve_resident.argtypes = [C.c_void_p, C.c_void_p]
@@ -147,6 +148,9 @@ class Context:
         res, cr, trace = into if into is not None else BAResult.alloc(self._problem, schedule.max_trace)
         self._check(self.lib.bagpu_solve_resident(self.h, C.byref(cs), C.byref(cr)))
         return res.finish(cr, trace)
+
+    def reset_resident(self):
+        self._check(self.lib.bagpu_reset_resident(self.h))
 
     # -- PoseOptimization
     def pose_opt_batch(self, batch: PoseBatch) -> PoseResult:

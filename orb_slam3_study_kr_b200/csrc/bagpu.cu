@@ -94,7 +94,7 @@ struct bagpu_ctx {
     bool identity_perm = true;
     DevBuf d_lm_ptr, d_o_pose, d_o_point, d_o_meta, d_o_u, d_o_v, d_o_ur, d_o_w, d_cams, d_rigs, d_hidx, d_perm;
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
-    DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b;
+    DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -268,7 +268,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
-                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_sys, &ctx->d_xp,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -412,6 +412,10 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     }
     h2d += (4 + 4 + 8 + 8 + 8 + (p->obs_ur ? 8 : 0)) * Ne;
     CK(cudaGetLastError());
+    // snapshot of the initial estimates / edge flags for bagpu_reset_resident
+    CK(ctx->d_pt_init.ensure(sizeof(double) * 3 * (size_t)Np)); CK(ctx->d_meta_init.ensure(4 * ne));
+    CK(cudaMemcpyAsync(ctx->d_pt_init.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_meta_init.p, ctx->d_o_meta.p, 4 * ne, cudaMemcpyDeviceToDevice, st));
 
     // --- reduced camera system buffers
     const int n = 6 * nf;
@@ -645,6 +649,22 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
         if (rc) return rc;
     }
     return status;
+}
+
+int bagpu_reset_resident(bagpu_ctx *ctx) {
+    if (!ctx) return BAGPU_ERR_ARG;
+    if (!ctx->have_problem) return fail(ctx, BAGPU_ERR_ARG, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->pose_cur = ctx->d_pose_a.as<double>(); ctx->pose_trial = ctx->d_pose_b.as<double>();
+    ctx->pt_cur = ctx->d_pt_a.as<double>(); ctx->pt_trial = ctx->d_pt_b.as<double>();
+    CK(cudaMemcpyAsync(ctx->pose_cur, ctx->d_pose_init.p, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->pose_trial, ctx->d_pose_init.p, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->pt_cur, ctx->d_pt_init.p, sizeof(double) * 3 * (size_t)ctx->n_points, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_meta.p, ctx->d_meta_init.p, 4 * (size_t)ctx->n_obs, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * (size_t)ctx->n_obs, st));
+    CK(cudaStreamSynchronize(st));
+    return BAGPU_OK;
 }
 
 int bagpu_download(bagpu_ctx *ctx, bagpu_result *r) {

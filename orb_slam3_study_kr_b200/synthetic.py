@@ -98,11 +98,15 @@ def _levels(rng, n, n_levels=8):
 # --------------------------------------------------------------------------- BA maps
 def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_track: float, sensor: str,
                     step: float = 0.15, dyaw_deg: float = 3.0, window: int = 80, outlier_frac: float = 0.05,
-                    robust: bool = True, stereo_frac: float = 0.7, name: str = "", chunk: int = 20000) -> BAProblem:
+                    robust: bool = True, stereo_frac: float = 0.7, name: str = "", chunk: int = 20000,
+                    shard: int = 0) -> BAProblem:
     """sensor: 'mono' (TUM1 pinhole), 'stereo' (EuRoC pinhole, mixed mono/stereo edges), 'fisheye' (TUM-VI KB8 rig:
-    left mono edges + right ToBody edges). The first `n_fixed` keyframes (oldest ids) are fixed."""
-    rng = np.random.default_rng(seed)
-    R_cw, t_cw = _trajectory(n_kf, step, dyaw_deg, rng)
+    left mono edges + right ToBody edges). The first `n_fixed` keyframes (oldest ids) are fixed.
+    Keyframes (trajectory and initial-pose perturbation) depend on `seed` only; landmarks and observations depend on
+    (`seed`, `shard`), so rank r of a multi-GPU run can generate ITS landmark shard of one common map directly."""
+    rng_kf = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, 7919 + shard])
+    R_cw, t_cw = _trajectory(n_kf, step, dyaw_deg, rng_kf)
     camL = {"mono": TUM1, "stereo": EUROC, "fisheye": TUMVI_L}[sensor]
     cams = [camL]
     rigs = None
@@ -124,9 +128,11 @@ def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_t
     offs_all = np.arange(-window, window + 1)
     P_all, cols = [], {k: [] for k in ("pose", "point", "cam", "rig", "kind", "u", "v", "ur", "lvl")}
     n_done = 0
+    # MapPoint ids grow with the keyframe that created them: landmarks come in creation (anchor keyframe) order
+    k0_all = np.sort(rng.integers(lo_anchor, n_kf, n_points))
     while n_done < n_points:
         pc = min(chunk, n_points - n_done)
-        k0 = rng.integers(lo_anchor, n_kf, pc)
+        k0 = k0_all[n_done:n_done + pc]
         d = rng.uniform(2.0, 12.0, pc)
         if camL["type"] == CAM_PINHOLE:
             uu = rng.uniform(20, camL["w"] - 20, pc)
@@ -204,7 +210,7 @@ def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_t
     ur = np.where((obs["kind"] == EDGE_STEREO) & (ur < 0), 0.0, ur)
 
     Pw = np.concatenate(P_all)
-    Ri, ti = _perturb(R_cw, t_cw, rng, 0.5, 0.01)
+    Ri, ti = _perturb(R_cw, t_cw, rng_kf, 0.5, 0.01)
     fixed = np.zeros(n_kf, np.uint8)
     fixed[:n_fixed] = 1
     Ri[:n_fixed], ti[:n_fixed] = R_cw[:n_fixed], t_cw[:n_fixed]
@@ -241,13 +247,25 @@ def config(n: int, scale: float = 1.0, robust: bool = True) -> BAProblem:
     raise ValueError(n)
 
 
-def global_ba_weak(n_ranks: int, seed: int = 4, n_kf: int = 500, points_per_rank: int = 200000,
-                   robust: bool = False) -> BAProblem:
-    """Weak-scaling global BA: keyframes fixed at `n_kf`, landmarks/observations grow with the rank count
-    (each rank owns `points_per_rank` landmarks = C4's per-GPU work)."""
-    return make_ba_problem(seed=seed, n_kf=n_kf, n_fixed=1, n_points=points_per_rank * n_ranks, mean_track=10.0,
-                           sensor="stereo", window=80, dyaw_deg=0.6, robust=robust,
-                           name=f"C4 global BA x{n_ranks} landmarks")
+def global_ba_shard(rank: int, n_ranks: int, seed: int = 4, n_kf: int = 500, points_per_rank: int = 200000,
+                    robust: bool = False) -> BAProblem:
+    """Weak-scaling global BA: the C4 keyframes (`n_kf`, one fixed) are common to all ranks; rank r owns
+    `points_per_rank` landmarks of its own (= C4's per-GPU work) and all of their observations. Rank 0 of a
+    1-rank run is exactly config(4)."""
+    return make_ba_problem(seed=seed, n_kf=n_kf, n_fixed=1, n_points=points_per_rank, mean_track=10.0,
+                           sensor="stereo", window=80, dyaw_deg=0.6, robust=robust, shard=rank,
+                           name=f"C4 global BA, landmark shard {rank}/{n_ranks}")
+
+
+def concat_shards(shards) -> BAProblem:
+    """The single-GPU view of a sharded map: same keyframes, landmarks and observations concatenated."""
+    p0 = shards[0]
+    off = np.cumsum([0] + [s.n_points for s in shards[:-1]])
+    cat = lambda k: np.concatenate([getattr(s, k) for s in shards])
+    return BAProblem(p0.pose_qt, p0.pose_fixed, cat("points"), p0.cameras, p0.rigs, cat("obs_pose"),
+                     np.concatenate([s.obs_point + o for s, o in zip(shards, off)]), cat("obs_cam"), cat("obs_rig"),
+                     cat("obs_kind"), cat("obs_flags"), cat("obs_u"), cat("obs_v"), cat("obs_ur"), cat("obs_inv_sigma2"),
+                     name="concat of %d shards" % len(shards))
 
 
 # --------------------------------------------------------------------------- PoseOptimization batch
