@@ -231,6 +231,9 @@ int  bagpu_get_timing(const bagpu_ctx *ctx, bagpu_timing *out);
 
 /* Device self-test hooks used by tests (libm parity of the float fossils). */
 int  bagpu_test_atan2f(bagpu_ctx *ctx, const float *y, const float *x, float *out, int64_t n);
+/* (A + lambda I) x = b with the production solver; A dense symmetric row-major, col_end[j] = last nonzero row of column j
+ * (monotone). fail_out = 1 when a pivot was not positive. */
+int  bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, double *x, int *fail_out);
 
 #ifdef __cplusplus
 }

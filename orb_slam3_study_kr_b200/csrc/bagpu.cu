@@ -96,6 +96,8 @@ struct bagpu_ctx {
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
+    DevBuf d_y, d_colend, d_dinv;
+    size_t s_elems = 0; int chol_grid = 1; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
     std::vector<int> h_hidx;
@@ -268,7 +270,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
-                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -296,7 +298,9 @@ int bagpu_comm_init(bagpu_ctx *ctx, int world_size, int rank, const uint8_t id[1
     CK(cudaSetDevice(ctx->device));
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
+    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] ncclCommInitRank world %d dev %d ...\n", rank, world_size, ctx->device);
     CKN(g_nccl.CommInitRank(&ctx->comm, world_size, uid, rank));
+    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] ncclCommInitRank done\n", rank);
     ctx->world = world_size; ctx->rank = rank;
     return BAGPU_OK;
 }
@@ -417,11 +421,63 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_pt_init.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_meta_init.p, ctx->d_o_meta.p, 4 * ne, cudaMemcpyDeviceToDevice, st));
 
-    // --- reduced camera system buffers
+    // --- reduced camera system: envelope of Hschur from the landmark structure, band or dense storage
     const int n = 6 * nf;
-    ctx->n_sys = n; ctx->ld = (n + 1 + 3) & ~3;
-    CK(ctx->d_sys.ensure(sizeof(double) * ((size_t)std::max(1, n) * ctx->ld + 3 * (size_t)std::max(1, n))));
+    ctx->n_sys = n;
+    {
+        std::vector<int> lastrow(std::max(1, nf));
+        for (int h = 0; h < nf; h++) lastrow[h] = h;
+        for (int j = 0; j < Np; j++) {
+            int mx = -1;
+            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                const int e = sorted ? a : perm[a];
+                mx = std::max(mx, ctx->h_hidx[p->obs_pose[e]]);
+            }
+            if (mx < 0) continue;
+            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                const int e = sorted ? a : perm[a];
+                const int h = ctx->h_hidx[p->obs_pose[e]];
+                if (h >= 0) lastrow[h] = std::max(lastrow[h], mx);
+            }
+        }
+        if (ctx->world > 1 && nf > 0) {
+            // every rank must lay the reduced camera system out identically: the envelope is the union over the shards
+            CK(ctx->d_colend.ensure(sizeof(int) * (size_t)nf));
+            CK(cudaMemcpyAsync(ctx->d_colend.p, lastrow.data(), sizeof(int) * (size_t)nf, cudaMemcpyHostToDevice, st));
+            CKN(g_nccl.AllReduce(ctx->d_colend.p, ctx->d_colend.p, (size_t)nf, ncclInt32, ncclMax, ctx->comm, st));
+            CK(cudaMemcpyAsync(lastrow.data(), ctx->d_colend.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        int bwb = 0;
+        for (int h = 1; h < nf; h++) lastrow[h] = std::max(lastrow[h], lastrow[h - 1]);     // monotone: bounds the fill too
+        for (int h = 0; h < nf; h++) bwb = std::max(bwb, lastrow[h] - h);
+        ctx->band_blocks = bwb;
+        std::vector<int> col_end(std::max(1, n));
+        int max_below = 0;
+        int band = 6 * (bwb + 1);                            // max (i - j) + 1 inside the envelope ...
+        for (int h = 0; h < nf; h++) for (int r = 0; r < 6; r++) col_end[6 * h + r] = 6 * lastrow[h] + 5;
+        for (int p0 = 0; p0 < n; p0 += CH_NB) {
+            const int nb = std::min(CH_NB, n - p0);
+            const int rend = std::min(n - 1, col_end[p0 + nb - 1]);
+            max_below = std::max(max_below, rend - (p0 + nb) + 1);
+            band = std::max(band, rend - p0 + 1);            // ... and every column of a panel stores the panel's rows
+        }
+        ctx->ld = std::max(1, std::min(band - 1, n));        // band storage when it is narrower than the matrix
+        ctx->s_elems = (size_t)std::max(1, n) * (ctx->ld + 1) + 8;   // Lm(i,j) = S[j*ld + i], i in [j, j+band): last index (n-1)*(ld+1)
+        const int nt = (max_below + CH_TB - 1) / CH_TB;
+        int occ_c = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, chol_solve_kernel, CH_THREADS, 0));
+        if (occ_c < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
+        ctx->chol_grid = std::max(1, std::min(ctx->n_sm * std::min(occ_c, 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR)));
+        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d occ=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid, occ_c);
+        CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
+        CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                       // col_end is a stack vector
+    }
+    CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n))));
     CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
+    CK(ctx->d_y.ensure(sizeof(double) * (size_t)std::max(1, n)));
+    CK(ctx->d_dinv.ensure(sizeof(double) * (size_t)std::max(1, n)));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
@@ -446,6 +502,7 @@ namespace {
 
 int all_reduce_sum(bagpu_ctx *ctx, double *buf, size_t count) {
     if (ctx->world <= 1) return BAGPU_OK;
+    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] allreduce sum %zu\n", ctx->rank, count);
     CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
     return BAGPU_OK;
 }
@@ -465,14 +522,8 @@ int read_status(bagpu_ctx *ctx, double *out, int count) {
 }
 
 int launch_chol(bagpu_ctx *ctx, CholArgs &a) {
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_solve_kernel, CH_THREADS, 0));
-    if (occ < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
-    const int nt = (a.n + 1 + CH_TB - 1) / CH_TB;
-    const int want = std::max(1, nt * (nt + 1) / 2);
-    const int grid = std::max(1, std::min(ctx->n_sm * std::min(occ, 2), want));
     void *args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(ctx->chol_grid), dim3(CH_THREADS), args, 0, ctx->stream));
     return BAGPU_OK;
 }
 
@@ -481,7 +532,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
     const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid;
     double *S = ctx->d_sys.as<double>();
-    double *bp = S + (size_t)std::max(1, n) * ld, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
+    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
     double *parts = ctx->d_parts.as<double>();
     double *part_chi_b = parts, *part_max = parts + G, *part_chi_u = parts + 2 * G, *part_scale = parts + 3 * G;
     double *dstat = ctx->d_status.as<double>();
@@ -513,17 +564,17 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         bool first = true;
         do {
             // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
-            CK(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)std::max(1, n) * ld + 2 * (size_t)std::max(1, n)), st));
+            CK(cudaMemsetAsync(S, 0, sizeof(double) * (ctx->s_elems + 2 * (size_t)std::max(1, n)), st));
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max;
             { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
             ctx->tm.total_launches++;
             ctx->tm.edge_linearisations += n_active;
-            int rc = all_reduce_sum(ctx, S, (size_t)std::max(1, n) * ld + 2 * (size_t)std::max(1, n)); if (rc) return rc;
+            int rc = all_reduce_sum(ctx, S, ctx->s_elems + 2 * (size_t)std::max(1, n)); if (rc) return rc;
             if (n > 0) {
                 CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
-                ca.x = ctx->d_xp.as<double>(); ca.fail = ctx->d_fail.as<int>();
+                ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
                 { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca); if (rc) return rc; }
                 ctx->tm.total_launches++;
             }
@@ -597,7 +648,7 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
     ctx->tm.build_ms = ctx->tm.linsolve_ms = ctx->tm.update_ms = 0;
     ctx->tm.build_launches = ctx->tm.update_launches = ctx->tm.linsolve_launches = ctx->tm.total_launches = 0;
     ctx->tm.lm_iterations = ctx->tm.lm_trials = ctx->tm.edge_linearisations = ctx->tm.edge_evaluations = 0;
-    ctx->tm.pcg_iterations = 0; ctx->tm.schur_blocks = ctx->n_free * (ctx->n_free + 1) / 2;
+    ctx->tm.pcg_iterations = 0; ctx->tm.schur_blocks = (int)std::min<long long>((long long)ctx->n_free * (ctx->n_free + 1) / 2, (long long)ctx->n_free * (ctx->band_blocks + 1));
     CK(cudaEventRecord(ctx->ev_phase[0], st));
     if (r) { r->n_trace = 0; r->status = BAGPU_OK; }
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -816,6 +867,54 @@ int bagpu_pose_opt_batch(bagpu_ctx *ctx, const bagpu_pose_batch *b, bagpu_pose_r
 int bagpu_get_timing(const bagpu_ctx *ctx, bagpu_timing *out) {
     if (!ctx || !out) return BAGPU_ERR_ARG;
     *out = ctx->tm;
+    return BAGPU_OK;
+}
+
+// Unit-test hook for the reduced-system solver: dense symmetric A (row-major), envelope col_end, (A + lambda I) x = b.
+int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, double *x, int *fail_out) {
+    if (!ctx || n <= 0 || !col_end || !A || !b || !x) return BAGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int band = 1, max_below = 0;
+    for (int j = 0; j < n; j++) {
+        if (col_end[j] < j || col_end[j] >= n || (j && col_end[j] < col_end[j - 1])) return fail(ctx, BAGPU_ERR_ARG, "col_end must be monotone and >= j");
+        band = std::max(band, col_end[j] - j + 1);
+    }
+    for (int p0 = 0; p0 < n; p0 += CH_NB) {
+        const int nb = std::min(CH_NB, n - p0);
+        const int rend = std::min(n - 1, col_end[p0 + nb - 1]);
+        max_below = std::max(max_below, rend - (p0 + nb) + 1);
+        band = std::max(band, rend - p0 + 1);
+    }
+    const int ld = std::max(1, std::min(band - 1, n));
+    const size_t s_elems = (size_t)n * (ld + 1) + 8;
+    std::vector<double> hS(s_elems, 0.0);
+    for (int R = 0; R < n; R++) for (int C = R; C <= col_end[R]; C++) hS[(size_t)R * ld + C] = A[(size_t)R * n + C];
+    DevBuf dS, db, dz, dx, dy, dc, df, dd;
+    CK(dd.ensure(8 * (size_t)n));
+    CK(dS.ensure(8 * s_elems)); CK(db.ensure(8 * (size_t)n)); CK(dz.ensure(8 * (size_t)n)); CK(dx.ensure(8 * (size_t)n));
+    CK(dy.ensure(8 * (size_t)n)); CK(dc.ensure(4 * (size_t)n)); CK(df.ensure(16));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dS.p, hS.data(), 8 * s_elems, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db.p, b, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dz.p, 0, 8 * (size_t)n, st));
+    CK(cudaMemsetAsync(df.p, 0, 16, st));
+    CK(cudaMemcpyAsync(dc.p, col_end, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    const int nt = (max_below + CH_TB - 1) / CH_TB;
+    int occ_c = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, chol_solve_kernel, CH_THREADS, 0));
+    const int save = ctx->chol_grid;
+    ctx->chol_grid = std::max(1, std::min(ctx->n_sm * std::min(std::max(occ_c, 1), 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR)));
+    CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
+    ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.x = dx.as<double>(); ca.fail = df.as<int>();
+    int rc = launch_chol(ctx, ca);
+    ctx->chol_grid = save;
+    if (rc) return rc;
+    int hf = 0;
+    CK(cudaMemcpyAsync(x, dx.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hf, df.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (fail_out) *fail_out = hf;
+    dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
     return BAGPU_OK;
 }
 

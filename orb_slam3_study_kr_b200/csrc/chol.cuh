@@ -1,96 +1,143 @@
-// Reduced camera system solve  (Hschur + lambda I) x = bschur  by dense FP64 Cholesky, one cooperative launch.
-// Replaces LinearSolverEigen::solve / LinearSolverDense::solve (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124,
-// linear_solver_dense.h:64-111) for systems small/dense enough to factor directly.
+// Reduced camera system solve  (Hschur + lambda I) x = bschur  by FP64 Cholesky inside the ENVELOPE of Hschur,
+// one cooperative launch. Replaces LinearSolverEigen::solve / LinearSolverDense::solve
+// (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124, linear_solver_dense.h:64-111).
 //
 // Storage: the buffer the build kernel scatters into, element (R,C), R<=C at S[R*ld + C] (row-major upper), is read
-// here as a column-major LOWER matrix Lm(i,j) = S[j*ld + i], i>=j. Row n of that lower matrix (= "column n" of the
-// row-major view) carries the right-hand side, so the forward substitution L y = b falls out of the panel TRSMs.
-// Right-looking blocked algorithm, panel width CH_NB, two grid syncs per panel; backward substitution is
-// right-looking too (one grid sync per panel).
+// here as a column-major LOWER matrix Lm(i,j) = S[j*ld + i], i>=j. With ld = n+1 this is a dense matrix; with
+// ld = band-1 it is LAPACK-style band storage (only entries with i-j < band exist) -- same indexing, so neither
+// the build kernel nor this one cares which it is.
+//
+// Structure: covisibility in a SLAM map is local, so Hschur has a profile: col_end[j] is the last row that can be
+// nonzero in column j (monotone, so it bounds the fill of L too). A panel of CH_NB columns only touches rows up to
+// col_end of its last column: the TRSM and the trailing update skip everything below, which turns the O(n^3) dense
+// factorisation into O(n * envelope^2).
+//
+// Right-looking blocked algorithm. Per panel: every CTA factors the 32x32 diagonal block redundantly with ONE warp
+// holding the block in registers (no block-wide barriers), TRSMs its share of the rows below, grid sync, updates
+// its share of the trailing tiles, grid sync. The forward substitution rides along; the backward substitution
+// is left-looking and done by CTA 0 alone (no grid syncs).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 namespace cg = cooperative_groups;
 
 #define CH_NB 32
-#define CH_RT 64          // rows per TRSM tile (one thread per row)
 #define CH_TB 64          // trailing-update tile
 #define CH_THREADS 256
+#define CH_TR 128         // rows per TRSM pass (one thread per row)
+static_assert(32 * 128 <= 2 * 32 * (64 + 2), "Xs must fit in the Pi|Pj buffer");
 
 struct CholArgs {
     double *S; int n; int ld;
     double lambda;
     const double *bp, *bs;    // bschur = bp + bs
+    const int *col_end;       // [n] last possibly-nonzero row of column j (monotone non-decreasing, >= j)
+    double *y;                // [n] scratch: right-hand side -> forward-substituted
+    double *dinv;             // [n] scratch: 1 / L(j,j)
     double *x;                // [n] out
     int *fail;                // set to 1 on a non-positive pivot
 };
 
+// One warp factors the 32x32 SPD block held in shared memory (Ld[r][c], lower part). Rolled loops on purpose: the
+// fully unrolled register version was 180 KB of SASS and ran at instruction-fetch speed. The pivot chain is the
+// critical path of the whole solve, so it carries no FP64 division or sqrt: one rsqrt per pivot,
+// L(k,k) = d * rsqrt(d), L(i,k) = a(i,k) * rsqrt(d). invd[k] = 1/L(k,k). Rows/columns >= nb hold the identity.
+__device__ __forceinline__ bool warp_potrf32_smem(double (*Ld)[CH_NB + 1], double *invd, int lane) {
+    bool ok = true;
+    for (int k = 0; k < CH_NB; k++) {
+        const double dkk = Ld[k][k];
+        if (!(dkk > 0.0)) ok = false;
+        const double rs = rsqrt(dkk);
+        const double lik = Ld[lane][k] * rs;            // lane >= k meaningful
+        __syncwarp();
+        if (lane == k) { Ld[k][k] = dkk * rs; invd[k] = rs; }
+        else if (lane > k) Ld[lane][k] = lik;
+        __syncwarp();
+#pragma unroll 4
+        for (int j = k + 1; j < CH_NB; j++)
+            if (lane >= j) Ld[lane][j] -= lik * Ld[j][k];
+        __syncwarp();
+    }
+    return ok;
+}
+
 __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double Ld[CH_NB][CH_NB + 1];
-    __shared__ double Pi[CH_NB][CH_TB + 2];
-    __shared__ double Pj[CH_NB][CH_TB + 2];
+    __shared__ double Ld[CH_NB][CH_NB + 1];      // factored diagonal block, Ld[r][c] = L(r,c)
+    __shared__ double invd[CH_NB];
+    __shared__ double PP[2 * CH_NB * (CH_TB + 2)];             // phase A: Xs[32][128]; phase B: Pi | Pj
+    double (*Xs)[CH_TR] = reinterpret_cast<double (*)[CH_TR]>(PP);
+    double (*Pi)[CH_TB + 2] = reinterpret_cast<double (*)[CH_TB + 2]>(PP);
+    double (*Pj)[CH_TB + 2] = reinterpret_cast<double (*)[CH_TB + 2]>(PP + CH_NB * (CH_TB + 2));
+    __shared__ double ys[CH_NB];
     __shared__ int s_fail;
     double *S = a.S;
-    const int n = a.n, ld = a.ld, nrows = a.n + 1;
-    const int tid = threadIdx.x;
+    const int n = a.n, ld = a.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
 
     for (size_t j = gtid; j < (size_t)n; j += gthreads) {
         S[j * ld + j] += a.lambda;
-        S[j * ld + n] = a.bp[j] + a.bs[j];
+        a.y[j] = a.bp[j] + a.bs[j];
     }
     grid.sync();
 
     bool failed = false;
     for (int p0 = 0; p0 < n; p0 += CH_NB) {
         const int nb = min(CH_NB, n - p0);
-        // ---- phase A: factor the diagonal block (redundantly per CTA), TRSM the rows below
-        for (int i = tid; i < CH_NB * CH_NB; i += CH_THREADS) {
-            const int r = i % CH_NB, c = i / CH_NB;
-            Ld[r][c] = (r < nb && c < nb && r >= c) ? S[(size_t)(p0 + c) * ld + p0 + r] : 0.0;
-        }
+        const int rbase = p0 + nb;
+        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);     // last row this panel can touch
+        const int nbelow = max(0, rend - rbase + 1);
+        // ---- phase A: diagonal block (warp 0 of every CTA, in registers), then TRSM of the rows below
         if (tid == 0) s_fail = 0;
         __syncthreads();
-        for (int k = 0; k < nb; k++) {
-            if (tid == 0) {
-                const double d = Ld[k][k];
-                if (!(d > 0.0)) s_fail = 1;
-                Ld[k][k] = sqrt(d);
-            }
-            __syncthreads();
-            const double dk = Ld[k][k];
-            for (int i = k + 1 + tid; i < nb; i += CH_THREADS) Ld[i][k] /= dk;
-            __syncthreads();
-            // trailing update of the small block: element (i,j), k < j <= i
-            for (int idx = tid; idx < CH_NB * CH_NB; idx += CH_THREADS) {
-                const int i = idx / CH_NB, j = idx % CH_NB;
-                if (j > k && i >= j && i < nb) Ld[i][j] -= Ld[i][k] * Ld[j][k];
-            }
-            __syncthreads();
+        if (warp == 0) {
+            for (int j = 0; j < CH_NB; j++)
+                Ld[lane][j] = (lane < nb && j < nb) ? ((j <= lane) ? S[(size_t)(p0 + j) * ld + p0 + lane] : 0.0) : ((j == lane) ? 1.0 : 0.0);
+            __syncwarp();
+            const bool ok = warp_potrf32_smem(Ld, invd, lane);
+            if (!ok && lane == 0) s_fail = 1;
         }
-        if (s_fail) { failed = true; }
-        if (failed) break;        // every CTA factors the same block: uniform exit
-        const int rbase = p0 + nb;
-        const int nbelow = nrows - rbase;
-        const int ntile = (nbelow + CH_RT - 1) / CH_RT;
-        for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-            const int r = rbase + t * CH_RT + tid;
-            if (tid < CH_RT && r < nrows) {
-                double xr[CH_NB];
+        __syncthreads();
+        if (s_fail) failed = true;
+        if (failed) break;                                        // every CTA factors the same block: uniform exit
+        if (blockIdx.x == 0 && warp == 1) {
+            // forward substitution rides along: y_p = L11^{-1} y_p (lane = row; sequential over columns)
+            double v = (lane < nb) ? a.y[p0 + lane] : 0.0;
+            for (int k = 0; k < nb; k++) {
+                const double yk = __shfl_sync(0xffffffffu, v, k) * invd[k];
+                if (lane == k) v = yk;
+                else if (lane > k) v -= Ld[lane][k] * yk;
+            }
+            if (lane < nb) a.y[p0 + lane] = v;
+        }
+        for (int r0 = blockIdx.x * CH_TR; r0 < nbelow; r0 += gridDim.x * CH_TR) {
+            // X L11^T = A21, one thread per row. Columns are solved in chunks of 8 held in registers; finished chunks sit
+            // in shared memory as Xs[k][thread] so the rolled update loop reads them without bank conflicts.
+            const int r = rbase + r0 + tid;
+            const bool act = tid < CH_TR && r <= rend;
+            if (tid < CH_TR)
+            for (int kb = 0; kb < CH_NB; kb += 8) {
+                double xr[8];
 #pragma unroll
-                for (int j = 0; j < CH_NB; j++) xr[j] = (j < nb) ? S[(size_t)(p0 + j) * ld + r] : 0.0;
+                for (int j = 0; j < 8; j++) xr[j] = (act && kb + j < nb) ? S[(size_t)(p0 + kb + j) * ld + r] : 0.0;
+                for (int m = 0; m < kb; m++) {
+                    const double xm = Xs[m][tid];
 #pragma unroll
-                for (int j = 0; j < CH_NB; j++) {
-                    if (j < nb) {
-                        double s = xr[j];
-#pragma unroll
-                        for (int k = 0; k < j; k++) s -= xr[k] * Ld[j][k];
-                        xr[j] = s / Ld[j][j];
-                    }
+                    for (int j = 0; j < 8; j++) xr[j] -= xm * Ld[kb + j][m];
                 }
 #pragma unroll
-                for (int j = 0; j < CH_NB; j++) if (j < nb) S[(size_t)(p0 + j) * ld + r] = xr[j];
+                for (int k = 0; k < 8; k++) {
+                    const double xk = xr[k] * invd[kb + k];
+                    xr[k] = xk;
+#pragma unroll
+                    for (int j = k + 1; j < 8; j++) xr[j] -= xk * Ld[kb + j][kb + k];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    Xs[kb + j][tid] = xr[j];
+                    if (act && kb + j < nb) S[(size_t)(p0 + kb + j) * ld + r] = xr[j];
+                }
             }
         }
         grid.sync();
@@ -100,8 +147,18 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
                 const int r = i % CH_NB, c = i / CH_NB;
                 if (r < nb && c < nb && r >= c) S[(size_t)(p0 + c) * ld + p0 + r] = Ld[r][c];
             }
+            if (tid < nb) a.dinv[p0 + tid] = invd[tid];
+            // y_below -= L21 y_p
+            if (tid < CH_NB) ys[tid] = (tid < nb) ? a.y[p0 + tid] : 0.0;
+            __syncthreads();
+            for (int r = rbase + tid; r <= rend; r += CH_THREADS) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < CH_NB; k++) if (k < nb) s += S[(size_t)(p0 + k) * ld + r] * ys[k];
+                a.y[r] -= s;
+            }
         }
-        // ---- phase B: trailing update C(i,j) -= sum_k P(i,k) P(j,k) over the lower triangle (incl. the RHS row)
+        // ---- phase B: trailing update C(i,j) -= sum_k P(i,k) P(j,k) over the lower triangle inside the envelope
         if (nbelow > 0) {
             const int nt = (nbelow + CH_TB - 1) / CH_TB;
             const int ntri = nt * (nt + 1) / 2;
@@ -115,8 +172,8 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
                 __syncthreads();
                 for (int idx = tid; idx < CH_NB * CH_TB; idx += CH_THREADS) {
                     const int k = idx / CH_TB, i = idx % CH_TB;
-                    Pi[k][i] = (k < nb && ri + i < nrows) ? S[(size_t)(p0 + k) * ld + ri + i] : 0.0;
-                    Pj[k][i] = (k < nb && cj + i < nrows) ? S[(size_t)(p0 + k) * ld + cj + i] : 0.0;
+                    Pi[k][i] = (k < nb && ri + i <= rend) ? S[(size_t)(p0 + k) * ld + ri + i] : 0.0;
+                    Pj[k][i] = (k < nb && cj + i <= rend) ? S[(size_t)(p0 + k) * ld + cj + i] : 0.0;
                 }
                 __syncthreads();
                 double acc[4][4];
@@ -137,11 +194,11 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
                     const int c = cj + tx * 4 + v;
-                    if (c >= n) continue;
+                    if (c > rend) continue;
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int r = ri + ty * 4 + u;
-                        if (r < nrows && r >= c) S[(size_t)c * ld + r] -= acc[u][v];
+                        if (r <= rend && r >= c) S[(size_t)c * ld + r] -= acc[u][v];
                     }
                 }
             }
@@ -152,39 +209,45 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
         if (gtid == 0) *a.fail = 1;
         return;
     }
-    // ---- backward substitution L^T x = y, y = row n of the lower matrix
-    // y lives in the RHS row S[j*ld + n] (updated in place); final x goes to a.x (written by CTA 0 only).
+    // ---- backward substitution L^T x = y, left-looking, CTA 0 alone (the envelope keeps every panel's GEMV small)
+    if (blockIdx.x != 0) return;
+    double *part = &Pi[0][0];                    // [8][32] partial sums
     const int last = ((n - 1) / CH_NB) * CH_NB;
-    double *xs = &Pi[0][0];     // reuse shared memory: x of the current block
     for (int p0 = last; p0 >= 0; p0 -= CH_NB) {
         const int nb = min(CH_NB, n - p0);
+        const int rbase = p0 + nb;
+        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);
         __syncthreads();
-        for (int i = tid; i < CH_NB * CH_NB; i += CH_THREADS) {
-            const int r = i % CH_NB, c = i / CH_NB;
-            Ld[r][c] = (r < nb && c < nb && r >= c) ? S[(size_t)(p0 + c) * ld + p0 + r] : 0.0;
-        }
-        if (tid < CH_NB) xs[tid] = (tid < nb) ? S[(size_t)(p0 + tid) * ld + n] : 0.0;
-        __syncthreads();
-        if (tid < 32) {
-            // warp 0: x_p = D^{-T} y_p, lane = column; sequential over rows from the bottom
-            double v = xs[tid];
-            for (int i = nb - 1; i >= 0; i--) {
-                const double xi = __shfl_sync(0xffffffffu, v, i) / Ld[i][i];
-                if (tid == i) v = xi;
-                else if (tid < i) v -= Ld[i][tid] * xi;
+        // s_j = sum_{i=rbase..rend} L(i, p0+j) x_i : column-major, so warp w owns columns j = w, w+8, w+16, w+24 and its
+        // lanes stride over the rows (coalesced); butterfly-reduce per column.
+#pragma unroll
+        for (int c = 0; c < CH_NB / (CH_THREADS / 32); c++) {
+            const int j = warp + c * (CH_THREADS / 32);
+            double sacc = 0.0;
+            if (j < nb) {
+                const double *col = S + (size_t)(p0 + j) * ld;
+                for (int i = rbase + lane; i <= rend; i += 32) sacc += col[i] * a.x[i];
             }
-            xs[tid] = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane == 0) part[j] = sacc;
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < CH_NB; j++)
+                Ld[lane][j] = (lane < nb && j < nb && j <= lane) ? S[(size_t)(p0 + j) * ld + p0 + lane] : 0.0;
+            invd[lane] = (lane < nb) ? a.dinv[p0 + lane] : 1.0;
         }
         __syncthreads();
-        if (blockIdx.x == 0 && tid < nb) a.x[p0 + tid] = xs[tid];
-        // y_j -= sum_{i in block} Lm(p0+i, j) x_i  for j < p0
-        for (size_t j = gtid; j < (size_t)p0; j += gthreads) {
-            const double *col = S + j * ld + p0;
-            double s = 0.0;
-#pragma unroll 8
-            for (int i = 0; i < CH_NB; i++) if (i < nb) s += col[i] * xs[i];
-            S[j * ld + n] -= s;
+        if (warp == 0) {
+            double v = (lane < nb) ? a.y[p0 + lane] - part[lane] : 0.0;
+            // x_p = L11^{-T} v : lane = column, sequential over rows from the bottom, multiplications only
+            for (int i = nb - 1; i >= 0; i--) {
+                const double xi = __shfl_sync(0xffffffffu, v, i) * invd[i];
+                if (lane == i) v = xi;
+                else if (lane < i) v -= Ld[i][lane] * xi;
+            }
+            if (lane < nb) a.x[p0 + lane] = v;
         }
-        grid.sync();
     }
 }

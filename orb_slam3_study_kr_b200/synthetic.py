@@ -97,7 +97,7 @@ def _levels(rng, n, n_levels=8):
 
 # --------------------------------------------------------------------------- BA maps
 def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_track: float, sensor: str,
-                    step: float = 0.15, dyaw_deg: float = 3.0, window: int = 80, outlier_frac: float = 0.05,
+                    step: float = 0.15, dyaw_deg: float = 3.0, window: int = 40, outlier_frac: float = 0.05,
                     robust: bool = True, stereo_frac: float = 0.7, name: str = "", chunk: int = 20000,
                     shard: int = 0) -> BAProblem:
     """sensor: 'mono' (TUM1 pinhole), 'stereo' (EuRoC pinhole, mixed mono/stereo edges), 'fisheye' (TUM-VI KB8 rig:
@@ -157,11 +157,16 @@ def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_t
             vis_any = visL | visR
         else:
             vis_any = visL
-        nvis = vis_any.sum(1)
-        q = np.minimum(1.0, mean_track / np.maximum(nvis.mean(), 1.0))
-        if sensor == "fisheye":
-            q = q * 0.62                                                   # two edges per kept keyframe on average
-        keep = vis_any & (rng.random(vis_any.shape) < q)
+        # A MapPoint is tracked over a CONTIGUOUS run of the keyframes that can see it (with a few missed
+        # detections), around the keyframe that created it -- not over a random subset of them.
+        rank_w = np.cumsum(vis_any, 1)                                     # 1-based rank among visible keyframes
+        ra = rank_w[:, window]
+        n_kf_mean = mean_track / (0.9 * (1.6 if sensor == "fisheye" else 1.0))
+        run = 2 + rng.poisson(max(n_kf_mean - 2.0, 0.5), pc)
+        left = (rng.random(pc) * run).astype(np.int64)
+        lo_r = (ra - left)[:, None]
+        hi_r = lo_r + run[:, None] - 1
+        keep = vis_any & (rank_w >= lo_r) & (rank_w <= hi_r) & (rng.random(vis_any.shape) < 0.9)
         keep[np.arange(pc), window] |= vis_any[:, window]                  # the anchor keyframe always observes it
         pi, wi = np.nonzero(keep)                                          # point-major, keyframe ascending
         kf = kk[pi, wi]
@@ -225,25 +230,27 @@ def make_ba_problem(*, seed: int, n_kf: int, n_fixed: int, n_points: int, mean_t
 
 def config(n: int, scale: float = 1.0, robust: bool = True) -> BAProblem:
     """BASELINE.json configs 1-5 (index n). `scale` < 1 shrinks points/observations (parity-test sizes);
-    keyframe counts shrink only for the global-BA configs."""
+    keyframe counts shrink only for the global-BA configs. `mean_track` below is the generator's run-length
+    parameter, calibrated so that the OBSERVATION counts hit BASELINE's (~40k, ~120k, ~110k, ~2M, ~20M): runs are
+    clipped by the window's ends and by visibility, so the realised mean track is shorter than the parameter."""
     s = scale
     if n == 1:
-        return make_ba_problem(seed=1, n_kf=30, n_fixed=10, n_points=max(50, int(5000 * s)), mean_track=8.0,
+        return make_ba_problem(seed=1, n_kf=30, n_fixed=10, n_points=max(50, int(5000 * s)), mean_track=14.0,
                                sensor="mono", window=30, name="C1 mono pinhole local BA")
     if n == 2:
-        return make_ba_problem(seed=2, n_kf=70, n_fixed=25, n_points=max(50, int(12000 * s)), mean_track=10.0,
+        return make_ba_problem(seed=2, n_kf=70, n_fixed=25, n_points=max(50, int(12000 * s)), mean_track=12.8,
                                sensor="stereo", window=70, dyaw_deg=1.5, name="C2 stereo pinhole local BA")
     if n == 3:
-        return make_ba_problem(seed=3, n_kf=45, n_fixed=15, n_points=max(50, int(8000 * s)), mean_track=8.5,
+        return make_ba_problem(seed=3, n_kf=45, n_fixed=15, n_points=max(50, int(8000 * s)), mean_track=12.0,
                                sensor="fisheye", window=45, dyaw_deg=2.0, name="C3 fisheye KB8 rig local BA")
     if n == 4:
         nk = max(12, int(500 * s))
-        return make_ba_problem(seed=4, n_kf=nk, n_fixed=1, n_points=max(100, int(200000 * s)), mean_track=10.0,
-                               sensor="stereo", window=80, dyaw_deg=0.6, robust=robust, name="C4 global BA")
+        return make_ba_problem(seed=4, n_kf=nk, n_fixed=1, n_points=max(100, int(200000 * s)), mean_track=11.2,
+                               sensor="stereo", window=40, dyaw_deg=0.6, robust=robust, name="C4 global BA")
     if n == 5:
         nk = max(24, int(5000 * s))
-        return make_ba_problem(seed=5, n_kf=nk, n_fixed=1, n_points=max(200, int(2000000 * s)), mean_track=10.0,
-                               sensor="stereo", window=80, dyaw_deg=0.06, robust=robust, name="C5 large global BA")
+        return make_ba_problem(seed=5, n_kf=nk, n_fixed=1, n_points=max(200, int(2000000 * s)), mean_track=11.2,
+                               sensor="stereo", window=40, dyaw_deg=0.06, robust=robust, name="C5 large global BA")
     raise ValueError(n)
 
 
@@ -252,8 +259,8 @@ def global_ba_shard(rank: int, n_ranks: int, seed: int = 4, n_kf: int = 500, poi
     """Weak-scaling global BA: the C4 keyframes (`n_kf`, one fixed) are common to all ranks; rank r owns
     `points_per_rank` landmarks of its own (= C4's per-GPU work) and all of their observations. Rank 0 of a
     1-rank run is exactly config(4)."""
-    return make_ba_problem(seed=seed, n_kf=n_kf, n_fixed=1, n_points=points_per_rank, mean_track=10.0,
-                           sensor="stereo", window=80, dyaw_deg=0.6, robust=robust, shard=rank,
+    return make_ba_problem(seed=seed, n_kf=n_kf, n_fixed=1, n_points=points_per_rank, mean_track=11.2,
+                           sensor="stereo", window=40, dyaw_deg=0.6, robust=robust, shard=rank,
                            name=f"C4 global BA, landmark shard {rank}/{n_ranks}")
 
 
