@@ -574,7 +574,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             int rc = all_reduce_sum(ctx, S, ctx->s_elems + 2 * (size_t)std::max(1, n)); if (rc) return rc;
             if (n > 0) {
                 CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
-                ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
+                ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
                 { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca); if (rc) return rc; }
                 ctx->tm.total_launches++;
             }
@@ -892,7 +892,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     DevBuf dS, db, dz, dx, dy, dc, df, dd;
     CK(dd.ensure(8 * (size_t)n));
     CK(dS.ensure(8 * s_elems)); CK(db.ensure(8 * (size_t)n)); CK(dz.ensure(8 * (size_t)n)); CK(dx.ensure(8 * (size_t)n));
-    CK(dy.ensure(8 * (size_t)n)); CK(dc.ensure(4 * (size_t)n)); CK(df.ensure(16));
+    CK(dy.ensure(8 * (size_t)n)); CK(dc.ensure(4 * (size_t)n)); CK(df.ensure(16 + 64));
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(dS.p, hS.data(), 8 * s_elems, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(db.p, b, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -905,7 +905,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     const int save = ctx->chol_grid;
     ctx->chol_grid = std::max(1, std::min(ctx->n_sm * std::min(std::max(occ_c, 1), 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR)));
     CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
-    ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.x = dx.as<double>(); ca.fail = df.as<int>();
+    ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = getenv("BAGPU_DEBUG") ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
     int rc = launch_chol(ctx, ca);
     ctx->chol_grid = save;
     if (rc) return rc;
@@ -914,6 +914,13 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemcpyAsync(&hf, df.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (fail_out) *fail_out = hf;
+    if (getenv("BAGPU_DEBUG")) {
+        long long hp[8];
+        cudaMemcpy(hp, (char *)df.p + 16, 64, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d: potrf %lld trsm %lld sync1 %lld wb+y %lld update %lld sync2 %lld backward %lld\n",
+                n, ld, std::max(1, std::min(ctx->n_sm * std::min(std::max(occ_c, 1), 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR))),
+                hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+    }
     dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
     return BAGPU_OK;
 }

@@ -36,6 +36,7 @@ struct CholArgs {
     double *dinv;             // [n] scratch: 1 / L(j,j)
     double *x;                // [n] out
     int *fail;                // set to 1 on a non-positive pivot
+    long long *prof;          // optional [8] cycle counters of CTA 0 (potrf, trsm, sync1, writeback+y, update, sync2, backward)
 };
 
 // One warp factors the 32x32 SPD block held in shared memory (Ld[r][c], lower part). Rolled loops on purpose: the
@@ -83,6 +84,9 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
     grid.sync();
 
     bool failed = false;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+#define PROF_TICK(i) do { if (a.prof) { t1 = clock64(); pc[i] += t1 - t0; t0 = t1; } } while (0)
+    if (a.prof) t0 = clock64();
     for (int p0 = 0; p0 < n; p0 += CH_NB) {
         const int nb = min(CH_NB, n - p0);
         const int rbase = p0 + nb;
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
             if (!ok && lane == 0) s_fail = 1;
         }
         __syncthreads();
+        PROF_TICK(0);
         if (s_fail) failed = true;
         if (failed) break;                                        // every CTA factors the same block: uniform exit
         if (blockIdx.x == 0 && warp == 1) {
@@ -140,7 +145,10 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
                 }
             }
         }
+        __syncthreads();
+        PROF_TICK(1);
         grid.sync();
+        PROF_TICK(2);
         // the factored diagonal block goes back only now: during phase A other CTAs were still reading the original
         if (blockIdx.x == 0) {
             for (int i = tid; i < CH_NB * CH_NB; i += CH_THREADS) {
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
                 a.y[r] -= s;
             }
         }
+        PROF_TICK(3);
         // ---- phase B: trailing update C(i,j) -= sum_k P(i,k) P(j,k) over the lower triangle inside the envelope
         if (nbelow > 0) {
             const int nt = (nbelow + CH_TB - 1) / CH_TB;
@@ -203,7 +212,10 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
                 }
             }
         }
+        __syncthreads();
+        PROF_TICK(4);
         grid.sync();
+        PROF_TICK(5);
     }
     if (failed) {
         if (gtid == 0) *a.fail = 1;
@@ -250,4 +262,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
             if (lane < nb) a.x[p0 + lane] = v;
         }
     }
+    __syncthreads();
+    PROF_TICK(6);
+    if (a.prof && tid == 0) for (int i = 0; i < 8; i++) a.prof[i] = pc[i];
 }
