@@ -96,7 +96,8 @@ struct bagpu_ctx {
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
-    DevBuf d_y, d_colend, d_dinv;
+    DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_tasks, d_recoff, d_rec, d_batches;
+    int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, parts_stride = 1;
     size_t s_elems = 0; int chol_grid = 1; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -270,7 +271,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
-                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_tiles, &ctx->d_lmwide, &ctx->d_tasks, &ctx->d_recoff, &ctx->d_rec, &ctx->d_batches,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -309,6 +310,8 @@ int bagpu_pin_host(void *p, size_t bytes) { return cudaHostRegister(p, bytes, cu
 int bagpu_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? BAGPU_OK : BAGPU_ERR_CUDA; }
 
 // ------------------------------------------------------------------------------- upload
+namespace { int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out); }
+
 int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (!ctx) return BAGPU_ERR_ARG;
     int rc = validate_problem(ctx, p);
@@ -464,15 +467,104 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         }
         ctx->ld = std::max(1, std::min(band - 1, n));        // band storage when it is narrower than the matrix
         ctx->s_elems = (size_t)std::max(1, n) * (ctx->ld + 1) + 8;   // Lm(i,j) = S[j*ld + i], i in [j, j+band): last index (n-1)*(ld+1)
-        const int nt = (max_below + CH_TB - 1) / CH_TB;
-        int occ_c = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, chol_solve_kernel, CH_THREADS, 0));
-        if (occ_c < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
-        ctx->chol_grid = std::max(1, std::min(ctx->n_sm * std::min(occ_c, 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR)));
+        { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid); if (rc2) return rc2; }
+        const int occ_c = 0;
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d occ=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid, occ_c);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
         CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));                       // col_end is a stack vector
+    }
+    // --- plan of the tiled build (stage_kernel + apply_kernel): wide flags, record offsets, packed tasks, tiles, batches
+    {
+        std::vector<uint8_t> wide((size_t)Np, 0);
+        std::vector<unsigned> rec_off((size_t)Np + 1, 0);
+        std::vector<int> lo_of((size_t)Np, INT32_MAX), hi_of((size_t)Np, -1);
+        int nw = 0;
+        unsigned long long total = 0;
+        for (int j = 0; j < Np; j++) {
+            const int k = lm_ptr[j + 1] - lm_ptr[j];
+            int lo = INT32_MAX, hi = -1, run = 0, prevh = -2, ndist = 0;
+            bool w = k > 32;
+            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                const int h = ctx->h_hidx[p->obs_pose[sorted ? a : perm[a]]];
+                if (h < 0) { prevh = -2; continue; }
+                lo = std::min(lo, h); hi = std::max(hi, h);
+                run = (h == prevh) ? run + 1 : 1;
+                if (run == 1) ndist++;
+                if (run > 2) w = true;                       // more than two edges on one (pose, point) pair
+                prevh = h;
+            }
+            if (hi >= 0 && hi - lo + 1 > BT_MW) w = true;
+            if (ndist > BT_KT) w = true;                     // more distinct cameras than a record holds
+            lo_of[j] = lo; hi_of[j] = hi;
+            rec_off[j] = (unsigned)total;
+            if (w) { wide[j] = 1; nw++; }
+            else if (k > 0) total += (unsigned long long)(BT_HDR + (ndist + 1) / 2 + 45 * ndist);
+        }
+        rec_off[Np] = (unsigned)total;
+        const bool tiled_ok = total < 0xffffffffull && n > 0;
+        std::vector<int2> tasks;
+        std::vector<TileInfo> tiles;
+        std::vector<BatchInfo> batches;
+        if (tiled_ok) {
+            // tasks: runs of whole non-wide landmarks with <= 32 observations in total
+            int tb = -1, tobs = 0;
+            for (int j = 0; j <= Np; j++) {
+                const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
+                const bool brk = j == Np || wide[j];
+                if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
+                if (!brk) { if (tb < 0) tb = j; tobs += k; }
+            }
+            // tiles: runs of landmarks whose free cameras fit a window of BT_MW pose indices
+            const int tl_max = std::max(16, std::min(256, Np / (2 * ctx->n_sm)));
+            int begin = 0, cur_lo = INT32_MAX, cur_hi = -1, cur_cnt = 0;
+            auto close_tile = [&](int end) {
+                if (cur_cnt > 0) {
+                    TileInfo T; T.begin = begin; T.end = end; T.cbase = (cur_hi >= 0) ? cur_lo : 0; T.pad = 0;
+                    T.batch_begin = (int)batches.size();
+                    int bb = begin; unsigned bspan = 0;
+                    for (int j = begin; j <= end; j++) {
+                        const unsigned sz = (j < end) ? rec_off[j + 1] - rec_off[j] : 0;
+                        if (j == end || bspan + sz > AP_STG_DOUBLES || j - bb >= AP_MAX_LM) {
+                            if (j > bb) { BatchInfo B; B.lm_begin = bb; B.lm_end = j; batches.push_back(B); }
+                            bb = j; bspan = 0;
+                        }
+                        bspan += sz;
+                    }
+                    T.batch_end = (int)batches.size();
+                    tiles.push_back(T);
+                }
+                begin = end; cur_lo = INT32_MAX; cur_hi = -1; cur_cnt = 0;
+            };
+            for (int j = 0; j < Np; j++) {
+                if (wide[j]) { cur_cnt++; continue; }       // stays inside the tile's range; it has no record
+                if (hi_of[j] >= 0) {
+                    const int nlo = std::min(cur_lo, lo_of[j]), nhi = std::max(cur_hi, hi_of[j]);
+                    if (cur_cnt > 0 && (nhi - nlo + 1 > BT_MW || cur_cnt >= tl_max)) close_tile(j);
+                    cur_lo = std::min(cur_lo, lo_of[j]); cur_hi = std::max(cur_hi, hi_of[j]);
+                } else if (cur_cnt >= tl_max) close_tile(j);
+                cur_cnt++;
+            }
+            close_tile(Np);
+        }
+        ctx->n_tiles = (int)tiles.size(); ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
+        CK(ctx->d_lmwide.ensure((size_t)Np));
+        CK(cudaMemcpyAsync(ctx->d_lmwide.p, wide.data(), (size_t)Np, cudaMemcpyHostToDevice, st));
+        if (ctx->n_tiles > 0) {
+            CK(ctx->d_tiles.ensure(sizeof(TileInfo) * tiles.size())); CK(ctx->d_batches.ensure(sizeof(BatchInfo) * std::max<size_t>(1, batches.size())));
+            CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size()))); CK(ctx->d_recoff.ensure(sizeof(unsigned) * ((size_t)Np + 1)));
+            CK(ctx->d_rec.ensure(sizeof(double) * std::max<unsigned long long>(1, total)));
+            CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, st));
+            if (!batches.empty()) CK(cudaMemcpyAsync(ctx->d_batches.p, batches.data(), sizeof(BatchInfo) * batches.size(), cudaMemcpyHostToDevice, st));
+            if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_recoff.p, rec_off.data(), sizeof(unsigned) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
+            int occ_st = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_st, stage_kernel, ST_THREADS, 0));
+            ctx->stage_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_st), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
+        }
+        CK(cudaStreamSynchronize(st));
+        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] tiled build: tiles=%d batches=%zu tasks=%d wide=%d records=%.1f MB stage_grid=%d\n",
+                                           ctx->n_tiles, batches.size(), ctx->n_tasks, nw, total * 8.0 / 1e6, ctx->stage_grid);
     }
     CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n))));
     CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
@@ -481,8 +573,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
-    CK(ctx->d_parts.ensure(sizeof(double) * 4 * (size_t)ctx->build_grid));
-    CK(ctx->d_status.ensure(sizeof(double) * 16));
+    ctx->parts_stride = std::max(ctx->build_grid, ctx->stage_grid);
+    CK(ctx->d_parts.ensure(sizeof(double) * 5 * (size_t)ctx->parts_stride));
+    CK(ctx->d_status.ensure(sizeof(double) * 32));
     CK(ctx->d_fail.ensure(sizeof(int) * 4));
     CK(ctx->d_count.ensure(sizeof(unsigned long long) * 2));
     CK(ctx->h_status.ensure(sizeof(double) * 32));
@@ -521,20 +614,39 @@ int read_status(bagpu_ctx *ctx, double *out, int count) {
     return BAGPU_OK;
 }
 
-int launch_chol(bagpu_ctx *ctx, CholArgs &a) {
+size_t chol_dyn_smem(int n) { return n <= CH_MAX_SMEM_N ? sizeof(double) * (size_t)std::max(1, n) : 0; }
+
+// cooperative grid for a system whose widest panel has `max_below` rows under its diagonal block:
+// one CTA per trailing tile (or TRSM row pass) plus the CTA that owns the right-hand side
+int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
+        attr_set = true;
+    }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_solve_kernel, CH_THREADS, chol_dyn_smem(n)));
+    if (occ < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
+    const int nt = (max_below + CH_TB - 1) / CH_TB;
+    const int want = std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR);
+    *grid_out = std::max(1, std::min(ctx->n_sm * occ, want + (want > 0 ? 1 : 0)));
+    return BAGPU_OK;
+}
+
+int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid) {
     void *args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(ctx->chol_grid), dim3(CH_THREADS), args, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, chol_dyn_smem(a.n), ctx->stream));
     return BAGPU_OK;
 }
 
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
     cudaStream_t st = ctx->stream;
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
-    const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid;
+    const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid, PS = ctx->parts_stride;
     double *S = ctx->d_sys.as<double>();
     double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
     double *parts = ctx->d_parts.as<double>();
-    double *part_chi_b = parts, *part_max = parts + G, *part_chi_u = parts + 2 * G, *part_scale = parts + 3 * G;
+    double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS;
     double *dstat = ctx->d_status.as<double>();
     auto stop = [&]() { return s->stop_flag && *s->stop_flag; };
 
@@ -547,7 +659,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             // computeLambdaInit: tau * max diagonal of Hpp and Hll (optimization_algorithm_levenberg.cpp:171-185)
             CK(cudaMemsetAsync(hpp, 0, sizeof(double) * std::max(1, n), st));
             BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
-            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max;
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_wide = nullptr;
             { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
             ctx->tm.total_launches++;
             int rc = all_reduce_sum(ctx, hpp, std::max(1, n)); if (rc) return rc;
@@ -567,15 +679,56 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (ctx->s_elems + 2 * (size_t)std::max(1, n)), st));
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
-            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max;
-            { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_wide = nullptr;
+            const bool tiled = n > 0 && ctx->n_tiles > 0 && !getenv("BAGPU_NO_TILES");
+            bool have_wide_part = false;
+            int n_part_b = G;
+            {
+                ScopedEv ev(ctx, EV_BUILD);
+                if (tiled) {
+                    static bool attr_set = false;
+                    if (!attr_set) { CK(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * AP_SMEM_DOUBLES))); attr_set = true; }
+                    StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.rec_off = ctx->d_recoff.as<unsigned>();
+                    SA.rec = ctx->d_rec.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b;
+                    stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
+                    n_part_b = ctx->stage_grid;
+                    ApplyArgs AA; AA.tiles = ctx->d_tiles.as<TileInfo>(); AA.n_tiles = ctx->n_tiles; AA.batches = ctx->d_batches.as<BatchInfo>();
+                    AA.rec_off = ctx->d_recoff.as<unsigned>(); AA.rec = ctx->d_rec.as<double>(); AA.S = S; AA.ld = ld; AA.bp = bp; AA.bs = bs;
+                    apply_kernel<<<std::min(ctx->n_sm, ctx->n_tiles), AP_THREADS, sizeof(double) * AP_SMEM_DOUBLES, st>>>(AA);
+                    ctx->tm.total_launches++;
+                    if (ctx->n_wide > 0) {             // landmarks the window cannot hold: global-atomic path
+                        BuildOut OW = O; OW.part_chi2 = part_chi_w; OW.lm_wide = ctx->d_lmwide.as<uint8_t>();
+                        build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, OW);
+                        have_wide_part = true; ctx->tm.total_launches++;
+                    }
+                } else {
+                    build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O);
+                }
+            }
+            if (tiled && getenv("BAGPU_COMPARE")) {      // debug: the same system through the global-atomic kernel, compared element-wise
+                const size_t cnt = ctx->s_elems + 2 * (size_t)n;
+                std::vector<double> a(cnt), b2(cnt);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(a.data(), S, 8 * cnt, cudaMemcpyDeviceToHost);
+                cudaMemset(S, 0, 8 * cnt);
+                BuildOut OC = O; OC.lm_wide = nullptr; OC.part_chi2 = part_chi_w;
+                build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, OC);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(b2.data(), S, 8 * cnt, cudaMemcpyDeviceToHost);
+                cudaMemcpy(S, a.data(), 8 * cnt, cudaMemcpyHostToDevice);
+                double worst = 0; size_t wi = 0; int nbad = 0;
+                for (size_t i = 0; i < cnt; i++) { const double d = fabs(a[i] - b2[i]) / (1e-9 + fabs(b2[i])); if (d > 1e-9) nbad++; if (d > worst || a[i] != a[i]) { worst = d; wi = i; } }
+                const size_t R = wi / ld, Cc = wi % ld;
+                fprintf(stderr, "[bagpu] compare tiled vs atomic: worst rel %.3e at %zu (row %zu col %zu; S elems %zu) tiled %.6e atomic %.6e, %d elements differ\n",
+                        worst, wi, R, Cc, ctx->s_elems, a[wi], b2[wi], nbad);
+            }
             ctx->tm.total_launches++;
             ctx->tm.edge_linearisations += n_active;
             int rc = all_reduce_sum(ctx, S, ctx->s_elems + 2 * (size_t)std::max(1, n)); if (rc) return rc;
             if (n > 0) {
                 CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
                 ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
-                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca); if (rc) return rc; }
+                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca, ctx->chol_grid); if (rc) return rc; }
                 ctx->tm.total_launches++;
             }
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
@@ -586,7 +739,11 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             ctx->tm.total_launches += 2;
             ctx->tm.edge_linearisations += 0; ctx->tm.edge_evaluations += n_active;
             // dstat[0]=chi2 at the linearisation point, [1]=trial chi2, [2]=landmark part of scale, [4]=pose part of scale
-            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_chi_b, part_chi_u, nullptr, nullptr, nullptr, 0, dstat);
+            // dstat[0] = sum of the build partials (+ wide path), dstat[1] = sum of the update partials
+            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_b, part_chi_b, nullptr, nullptr, nullptr, nullptr, 0, dstat + 12, have_wide_part ? part_chi_w : nullptr, G);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(G, nullptr, part_chi_u, nullptr, nullptr, nullptr, 0, dstat);
+            CK(cudaMemcpyAsync(dstat, dstat + 12, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            ctx->tm.total_launches++;
             reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8);
             ctx->tm.total_launches += 2;
             CK(cudaMemcpyAsync(dstat + 2, dstat + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -899,15 +1056,11 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemsetAsync(dz.p, 0, 8 * (size_t)n, st));
     CK(cudaMemsetAsync(df.p, 0, 16, st));
     CK(cudaMemcpyAsync(dc.p, col_end, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    const int nt = (max_below + CH_TB - 1) / CH_TB;
-    int occ_c = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, chol_solve_kernel, CH_THREADS, 0));
-    const int save = ctx->chol_grid;
-    ctx->chol_grid = std::max(1, std::min(ctx->n_sm * std::min(std::max(occ_c, 1), 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR)));
+    int tgrid = 1;
+    { int rc2 = chol_plan_grid(ctx, n, max_below, &tgrid); if (rc2) return rc2; }
     CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
     ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = getenv("BAGPU_DEBUG") ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
-    int rc = launch_chol(ctx, ca);
-    ctx->chol_grid = save;
+    int rc = launch_chol(ctx, ca, tgrid);
     if (rc) return rc;
     int hf = 0;
     CK(cudaMemcpyAsync(x, dx.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -918,8 +1071,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
         long long hp[8];
         cudaMemcpy(hp, (char *)df.p + 16, 64, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d: potrf %lld trsm %lld sync1 %lld wb+y %lld update %lld sync2 %lld backward %lld\n",
-                n, ld, std::max(1, std::min(ctx->n_sm * std::min(std::max(occ_c, 1), 2), std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR))),
-                hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+                n, ld, tgrid, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
     }
     dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
     return BAGPU_OK;
