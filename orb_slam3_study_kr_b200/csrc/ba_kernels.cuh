@@ -540,6 +540,7 @@ struct UpdateOut {
     double *edge_chi2;            // [n_obs] (sorted order)
     double *part_chi2;            // [gridDim.x]
     double *part_scale;           // [gridDim.x]  sum over landmarks of x_l (lambda x_l + b_l)
+    const uint8_t *lm_wide;       // optional: update_kernel then handles only landmarks with lm_wide[j] != 0
 };
 
 __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const double *__restrict__ pose,
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const do
     double chi_acc = 0.0, sc_acc = 0.0;
     for (int j = gw; j < D.n_points; j += nw) {
         const int e0 = __ldg(D.lm_ptr + j), k = __ldg(D.lm_ptr + j + 1) - e0;
+        if (O.lm_wide && !O.lm_wide[j]) continue;
         const double X = __ldg(pt + 3 * (size_t)j), Y = __ldg(pt + 3 * (size_t)j + 1), Z = __ldg(pt + 3 * (size_t)j + 2);
         if (k == 0) {
             if (lane == 0) { O.pt_trial[3 * (size_t)j] = X; O.pt_trial[3 * (size_t)j + 1] = Y; O.pt_trial[3 * (size_t)j + 2] = Z; }
@@ -635,6 +637,114 @@ __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const do
     if (threadIdx.x == 0) {
         double c = 0.0, s = 0.0;
         for (int w = 0; w < BUILD_WARPS; w++) { c += s_chi[w]; s += s_sc[w]; }
+        O.part_chi2[blockIdx.x] = c;
+        O.part_scale[blockIdx.x] = s;
+    }
+}
+
+// update_packed_kernel: update_kernel with the lanes packed like stage_kernel (lane = observation, a task = a run of whole
+// landmarks with <= 32 observations, segmented reductions per landmark). Landmarks the tasks do not cover ("wide") go
+// through update_kernel with a mask.
+struct UpdateTasks { const int2 *tasks; int n_tasks; };
+
+__global__ void __launch_bounds__(ST_THREADS) update_packed_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt,
+                                                                  UpdateOut O, UpdateTasks K) {
+    __shared__ double s_chi[ST_WARPS], s_sc[ST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double chi_acc = 0.0, sc_acc = 0.0;
+    for (int t = blockIdx.x * ST_WARPS + warp; t < K.n_tasks; t += gridDim.x * ST_WARPS) {
+        const int2 tk = K.tasks[t];
+        const int e_first = __ldg(D.lm_ptr + tk.x), nobs = __ldg(D.lm_ptr + tk.y) - e_first;
+        const bool in = lane < nobs;
+        const int e = e_first + lane;
+        const int j = in ? __ldg(D.o_point + e) : -1;
+        int head = lane, segl = 1;
+        double X = 0, Y = 0, Z = 1;
+        if (in) {
+            const int p0 = __ldg(D.lm_ptr + j);
+            head = lane - (e - p0); segl = __ldg(D.lm_ptr + j + 1) - p0;
+            X = __ldg(pt + 3 * (size_t)j); Y = __ldg(pt + 3 * (size_t)j + 1); Z = __ldg(pt + 3 * (size_t)j + 2);
+        }
+        const int seg_last = head + segl - 1;
+        LaneEdge E;
+        lane_linearize(D, pose, X, Y, Z, e, in, E);
+        double r[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] = 0.0;
+        if (E.valid) {
+            const double *A = E.L.A, *B = E.L.B;
+            r[0] = E.wgt * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6]);
+            r[1] = E.wgt * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7]);
+            r[2] = E.wgt * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8]);
+            r[3] = E.wgt * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7]);
+            r[4] = E.wgt * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8]);
+            r[5] = E.wgt * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8]);
+            r[6] = A[0] * E.g0 + A[3] * E.g1 + A[6] * E.g2;
+            r[7] = A[1] * E.g0 + A[4] * E.g1 + A[7] * E.g2;
+            r[8] = A[2] * E.g0 + A[5] * E.g1 + A[8] * E.g2;
+            if (E.hidx >= 0) {
+                const double *x = O.xp + 6 * E.hidx;                    // W^T xp = wgt A^T (B xp)
+                double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) { const double xa = __ldg(x + a); s0 += B[a] * xa; s1 += B[6 + a] * xa; s2 += B[12 + a] * xa; }
+                r[9] = -E.wgt * (A[0] * s0 + A[3] * s1 + A[6] * s2);
+                r[10] = -E.wgt * (A[1] * s0 + A[4] * s1 + A[7] * s2);
+                r[11] = -E.wgt * (A[2] * s0 + A[5] * s1 + A[8] * s2);
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const bool take = in && lane + off <= seg_last;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const double o = __shfl_down_sync(0xffffffffu, r[i], off);
+                if (take) r[i] += o;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] = __shfl_sync(0xffffffffu, r[i], head);
+        const unsigned vmask = __ballot_sync(0xffffffffu, E.valid);
+        const unsigned segmask = (segl >= 32 ? 0xffffffffu : ((1u << segl) - 1u)) << head;
+        const bool any_act = (vmask & segmask) != 0u;
+        double nx = X, ny = Y, nz = Z;
+        if (in && any_act) {
+            double h[6] = {r[0] + O.lambda, r[1], r[2], r[3] + O.lambda, r[4], r[5] + O.lambda}, di[6];
+            sym3_inverse(h, di);
+            const double c0 = r[6] + r[9], c1 = r[7] + r[10], c2 = r[8] + r[11];
+            const double x0 = di[0] * c0 + di[1] * c1 + di[2] * c2;
+            const double x1 = di[1] * c0 + di[3] * c1 + di[4] * c2;
+            const double x2 = di[2] * c0 + di[4] * c1 + di[5] * c2;
+            nx = X + x0; ny = Y + x1; nz = Z + x2;
+            if (lane == head) sc_acc += x0 * (O.lambda * x0 + r[6]) + x1 * (O.lambda * x1 + r[7]) + x2 * (O.lambda * x2 + r[8]);
+        }
+        if (in && lane == head) { O.pt_trial[3 * (size_t)j] = nx; O.pt_trial[3 * (size_t)j + 1] = ny; O.pt_trial[3 * (size_t)j + 2] = nz; }
+        // evaluation at the trial state
+        if (E.valid) {
+            const uint32_t m = D.o_meta[e];
+            const int ip = __ldg(D.o_pose + e);
+            const int kind = META_KIND(m);
+            const Cam cam = load_cam(D.cams + META_CAM(m));
+            const Pose T = load_pose(O.pose_trial + 7 * (size_t)ip);
+            Pose Trl;
+            if (kind == BAGPU_EDGE_BODY) Trl = load_pose(D.rigs + 7 * META_RIG(m));
+            const double om = __ldg(D.o_w + e);
+            double r0, r1, r2;
+            edge_residual(kind, cam, T, &Trl, nx, ny, nz, __ldg(D.o_u + e), __ldg(D.o_v + e),
+                          (kind == BAGPU_EDGE_STEREO) ? __ldg(D.o_ur + e) : 0.0, false, r0, r1, r2);
+            const double chi2 = r0 * (om * r0) + r1 * (om * r1) + r2 * (om * r2);
+            O.edge_chi2[e] = chi2;
+            double rho0 = chi2, rho1;
+            if (m & META_ROBUST) huber(chi2, kind == BAGPU_EDGE_STEREO ? D.delta_stereo : D.delta_mono, rho0, rho1);
+            chi_acc += rho0;
+        }
+    }
+    chi_acc = warp_allsum(chi_acc);
+    sc_acc = warp_allsum(sc_acc);
+    if (lane == 0) { s_chi[warp] = chi_acc; s_sc[warp] = sc_acc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0, s = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) { c += s_chi[w]; s += s_sc[w]; }
         O.part_chi2[blockIdx.x] = c;
         O.part_scale[blockIdx.x] = s;
     }

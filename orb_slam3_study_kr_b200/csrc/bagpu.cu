@@ -97,7 +97,7 @@ struct bagpu_ctx {
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_tasks, d_recoff, d_rec, d_batches;
-    int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, parts_stride = 1;
+    int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, upd_grid = 1, parts_stride = 1;
     size_t s_elems = 0; int chol_grid = 1; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -371,6 +371,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_pose_b.p, ctx->d_pose_a.p, sizeof(double) * 7 * (size_t)Nt, cudaMemcpyDeviceToDevice, st));
     if (p->n_rigs) CK(cudaMemcpyAsync(ctx->d_rigs.p, hr, sizeof(double) * 7 * (size_t)p->n_rigs, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_pt_a.p, p->points, sizeof(double) * 3 * (size_t)Np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_pt_b.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));   // landmarks without observations are never rewritten
     CK(cudaMemcpyAsync(ctx->d_hidx.p, ctx->h_hidx.data(), sizeof(int) * (size_t)Nt, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_cams.p, p->cameras, sizeof(bagpu_camera) * (size_t)p->n_cameras, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_lm_ptr.p, lm_ptr.data(), sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
@@ -506,8 +507,8 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         std::vector<int2> tasks;
         std::vector<TileInfo> tiles;
         std::vector<BatchInfo> batches;
-        if (tiled_ok) {
-            // tasks: runs of whole non-wide landmarks with <= 32 observations in total
+        {
+            // tasks: runs of whole non-wide landmarks with <= 32 observations in total (stage_kernel, update_packed_kernel)
             int tb = -1, tobs = 0;
             for (int j = 0; j <= Np; j++) {
                 const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
@@ -515,6 +516,8 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
                 if (!brk) { if (tb < 0) tb = j; tobs += k; }
             }
+        }
+        if (tiled_ok) {
             // tiles: runs of landmarks whose free cameras fit a window of BT_MW pose indices
             const int tl_max = std::max(16, std::min(256, Np / (2 * ctx->n_sm)));
             int begin = 0, cur_lo = INT32_MAX, cur_hi = -1, cur_cnt = 0;
@@ -550,13 +553,19 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         ctx->n_tiles = (int)tiles.size(); ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
         CK(ctx->d_lmwide.ensure((size_t)Np));
         CK(cudaMemcpyAsync(ctx->d_lmwide.p, wide.data(), (size_t)Np, cudaMemcpyHostToDevice, st));
+        CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size())));
+        if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
+        {
+            int occ_u = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, update_packed_kernel, ST_THREADS, 0));
+            ctx->upd_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_u), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
+        }
         if (ctx->n_tiles > 0) {
             CK(ctx->d_tiles.ensure(sizeof(TileInfo) * tiles.size())); CK(ctx->d_batches.ensure(sizeof(BatchInfo) * std::max<size_t>(1, batches.size())));
-            CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size()))); CK(ctx->d_recoff.ensure(sizeof(unsigned) * ((size_t)Np + 1)));
+            CK(ctx->d_recoff.ensure(sizeof(unsigned) * ((size_t)Np + 1)));
             CK(ctx->d_rec.ensure(sizeof(double) * std::max<unsigned long long>(1, total)));
             CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, st));
             if (!batches.empty()) CK(cudaMemcpyAsync(ctx->d_batches.p, batches.data(), sizeof(BatchInfo) * batches.size(), cudaMemcpyHostToDevice, st));
-            if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(ctx->d_recoff.p, rec_off.data(), sizeof(unsigned) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
             int occ_st = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_st, stage_kernel, ST_THREADS, 0));
@@ -573,8 +582,8 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
-    ctx->parts_stride = std::max(ctx->build_grid, ctx->stage_grid);
-    CK(ctx->d_parts.ensure(sizeof(double) * 5 * (size_t)ctx->parts_stride));
+    ctx->parts_stride = std::max(std::max(ctx->build_grid, ctx->stage_grid), ctx->upd_grid);
+    CK(ctx->d_parts.ensure(sizeof(double) * 7 * (size_t)ctx->parts_stride));
     CK(ctx->d_status.ensure(sizeof(double) * 32));
     CK(ctx->d_fail.ensure(sizeof(int) * 4));
     CK(ctx->d_count.ensure(sizeof(unsigned long long) * 2));
@@ -646,7 +655,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
     double *S = ctx->d_sys.as<double>();
     double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
     double *parts = ctx->d_parts.as<double>();
-    double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS;
+    double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS,
+           *part_chi_uw = parts + 5 * PS, *part_scale_w = parts + 6 * PS;
     double *dstat = ctx->d_status.as<double>();
     auto stop = [&]() { return s->stop_flag && *s->stop_flag; };
 
@@ -734,18 +744,33 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
             UpdateOut U; U.lambda = lambda; U.xp = ctx->d_xp.as<double>(); U.pose_trial = ctx->pose_trial; U.pt_trial = ctx->pt_trial;
-            U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale;
-            { ScopedEv ev(ctx, EV_UPDATE); update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U); }
+            U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale; U.lm_wide = nullptr;
+            const bool packed = ctx->n_tasks > 0 && !getenv("BAGPU_NO_TILES");
+            int n_part_u = G; bool upd_wide = false;
+            {
+                ScopedEv ev(ctx, EV_UPDATE);
+                if (packed) {
+                    UpdateTasks K; K.tasks = ctx->d_tasks.as<int2>(); K.n_tasks = ctx->n_tasks;
+                    update_packed_kernel<<<ctx->upd_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U, K);
+                    n_part_u = ctx->upd_grid;
+                    if (ctx->n_wide > 0) {
+                        UpdateOut UW = U; UW.part_chi2 = part_chi_uw; UW.part_scale = part_scale_w; UW.lm_wide = ctx->d_lmwide.as<uint8_t>();
+                        update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, UW);
+                        upd_wide = true; ctx->tm.total_launches++;
+                    }
+                } else {
+                    update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U);
+                }
+            }
             ctx->tm.total_launches += 2;
             ctx->tm.edge_linearisations += 0; ctx->tm.edge_evaluations += n_active;
-            // dstat[0]=chi2 at the linearisation point, [1]=trial chi2, [2]=landmark part of scale, [4]=pose part of scale
-            // dstat[0] = sum of the build partials (+ wide path), dstat[1] = sum of the update partials
+            // dstat[0] = chi2 at the linearisation point, [1] = trial chi2, [2] = landmark part of scale, [4] = pose part of scale
             reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_b, part_chi_b, nullptr, nullptr, nullptr, nullptr, 0, dstat + 12, have_wide_part ? part_chi_w : nullptr, G);
-            reduce_partials_kernel<<<1, 256, 0, st>>>(G, nullptr, part_chi_u, nullptr, nullptr, nullptr, 0, dstat);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_chi_u, nullptr, nullptr, nullptr, nullptr, 0, dstat + 16, upd_wide ? part_chi_uw : nullptr, G);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8, upd_wide ? part_scale_w : nullptr, G);
+            ctx->tm.total_launches += 3;
             CK(cudaMemcpyAsync(dstat, dstat + 12, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            ctx->tm.total_launches++;
-            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8);
-            ctx->tm.total_launches += 2;
+            CK(cudaMemcpyAsync(dstat + 1, dstat + 16, sizeof(double), cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(dstat + 2, dstat + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(dstat + 5, ctx->d_fail.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
             rc = all_reduce_sum(ctx, dstat, 3); if (rc) return rc;
@@ -869,6 +894,7 @@ int bagpu_reset_resident(bagpu_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->pose_cur, ctx->d_pose_init.p, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->pose_trial, ctx->d_pose_init.p, sizeof(double) * 7 * (size_t)ctx->n_poses, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->pt_cur, ctx->d_pt_init.p, sizeof(double) * 3 * (size_t)ctx->n_points, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->pt_trial, ctx->d_pt_init.p, sizeof(double) * 3 * (size_t)ctx->n_points, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_o_meta.p, ctx->d_meta_init.p, 4 * (size_t)ctx->n_obs, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * (size_t)ctx->n_obs, st));
     CK(cudaStreamSynchronize(st));
