@@ -98,7 +98,7 @@ struct bagpu_ctx {
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_tasks, d_recoff, d_rec, d_batches;
     int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, upd_grid = 1, parts_stride = 1;
-    size_t s_elems = 0; int chol_grid = 1; int band_blocks = 0;
+    size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
     std::vector<int> h_hidx;
@@ -310,7 +310,7 @@ int bagpu_pin_host(void *p, size_t bytes) { return cudaHostRegister(p, bytes, cu
 int bagpu_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? BAGPU_OK : BAGPU_ERR_CUDA; }
 
 // ------------------------------------------------------------------------------- upload
-namespace { int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out); }
+namespace { int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out); }
 
 int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (!ctx) return BAGPU_ERR_ARG;
@@ -468,7 +468,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         }
         ctx->ld = std::max(1, std::min(band - 1, n));        // band storage when it is narrower than the matrix
         ctx->s_elems = (size_t)std::max(1, n) * (ctx->ld + 1) + 8;   // Lm(i,j) = S[j*ld + i], i in [j, j+band): last index (n-1)*(ld+1)
-        { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid); if (rc2) return rc2; }
+        { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid, &ctx->chol_maxr); if (rc2) return rc2; }
         const int occ_c = 0;
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d occ=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid, occ_c);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
@@ -625,26 +625,63 @@ int read_status(bagpu_ctx *ctx, double *out, int count) {
 
 size_t chol_dyn_smem(int n) { return n <= CH_MAX_SMEM_N ? sizeof(double) * (size_t)std::max(1, n) : 0; }
 
-// cooperative grid for a system whose widest panel has `max_below` rows under its diagonal block:
-// one CTA per trailing tile (or TRSM row pass) plus the CTA that owns the right-hand side
-int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out) {
+// Launch plan for a system whose widest panel has `max_below` rows under its diagonal block.
+//  * max_below + 32 <= CB_MAXR: chol_band_kernel, ONE cluster of NC = 2^k >= ceil(maxr / 32) CTAs (<= 16), the window of
+//    the factorisation in shared memory;
+//  * otherwise chol_solve_kernel: one CTA per trailing tile (or TRSM row pass) plus the CTA that owns the right-hand side;
+//    up to CH_CLUSTER_MAX CTAs as one cluster (hardware barrier), beyond that a cooperative launch.
+#define CH_CLUSTER_MAX 16
+size_t chol_band_smem(int maxr) { return sizeof(double) * 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
+
+int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out) {
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
+        CK(cudaFuncSetAttribute(chol_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
+        CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
+        CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_band_smem(CB_MAXR)));
+        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
+    static const bool no_band = getenv("BAGPU_NO_BAND") != nullptr;
+    const int maxr = max_below + CH_NB;
+    if (maxr <= CB_MAXR && !no_band) {
+        int nc = 1;
+        while (nc * CH_NB < maxr) nc *= 2;
+        *grid_out = nc; *maxr_out = maxr;
+        return BAGPU_OK;
+    }
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_solve_kernel, CH_THREADS, chol_dyn_smem(n)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_solve_kernel<false>, CH_THREADS, chol_dyn_smem(n)));
     if (occ < 1) return fail(ctx, BAGPU_ERR_CUDA, "cholesky kernel does not fit");
     const int nt = (max_below + CH_TB - 1) / CH_TB;
     const int want = std::max(nt * (nt + 1) / 2, (max_below + CH_TR - 1) / CH_TR);
     *grid_out = std::max(1, std::min(ctx->n_sm * occ, want + (want > 0 ? 1 : 0)));
+    *maxr_out = 0;
     return BAGPU_OK;
 }
 
-int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid) {
+int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr) {
+    static const bool no_cluster = getenv("BAGPU_NO_CLUSTER") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = grid; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.stream = ctx->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    if (maxr > 0) {
+        cfg.blockDim = dim3(CB_THREADS);
+        cfg.dynamicSmemBytes = chol_band_smem(maxr);
+        CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr));
+        return BAGPU_OK;
+    }
+    if (grid <= CH_CLUSTER_MAX && !no_cluster) {
+        cfg.blockDim = dim3(CH_THREADS);
+        cfg.dynamicSmemBytes = chol_dyn_smem(a.n);
+        CK(cudaLaunchKernelEx(&cfg, chol_solve_kernel<true>, a));
+        return BAGPU_OK;
+    }
     void *args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, chol_dyn_smem(a.n), ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel<false>, dim3(grid), dim3(CH_THREADS), args, chol_dyn_smem(a.n), ctx->stream));
     return BAGPU_OK;
 }
 
@@ -738,7 +775,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             if (n > 0) {
                 CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
                 ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
-                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca, ctx->chol_grid); if (rc) return rc; }
+                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr); if (rc) return rc; }
                 ctx->tm.total_launches++;
             }
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
@@ -1082,11 +1119,11 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemsetAsync(dz.p, 0, 8 * (size_t)n, st));
     CK(cudaMemsetAsync(df.p, 0, 16, st));
     CK(cudaMemcpyAsync(dc.p, col_end, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    int tgrid = 1;
-    { int rc2 = chol_plan_grid(ctx, n, max_below, &tgrid); if (rc2) return rc2; }
+    int tgrid = 1, tmaxr = 0;
+    { int rc2 = chol_plan_grid(ctx, n, max_below, &tgrid, &tmaxr); if (rc2) return rc2; }
     CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
     ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = getenv("BAGPU_DEBUG") ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
-    int rc = launch_chol(ctx, ca, tgrid);
+    int rc = launch_chol(ctx, ca, tgrid, tmaxr);
     if (rc) return rc;
     int hf = 0;
     CK(cudaMemcpyAsync(x, dx.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1096,8 +1133,8 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     if (getenv("BAGPU_DEBUG")) {
         long long hp[8];
         cudaMemcpy(hp, (char *)df.p + 16, 64, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d: potrf %lld trsm %lld sync1 %lld wb+y %lld update %lld sync2 %lld backward %lld\n",
-                n, ld, tgrid, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+        fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d maxr=%d: [0]potrf %lld [1]trsm %lld [2]sync1|wb+y %lld [3]wb+y|sync %lld [4]update %lld [5]sync2|take %lld [6]backward %lld\n",
+                n, ld, tgrid, tmaxr, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
     }
     dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
     return BAGPU_OK;

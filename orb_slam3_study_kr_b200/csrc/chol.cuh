@@ -103,8 +103,18 @@ __device__ __forceinline__ bool warp_potrf32_blocked(double (*Ld)[CH_NB + 1], do
     return ok;
 }
 
+// CL = false: cooperative launch, grid.sync() between phases (any grid up to the device).
+// CL = true : the whole grid is ONE thread-block cluster (<= 16 CTAs) and the phases are separated by the hardware
+//             cluster barrier (a few hundred cycles instead of a software grid barrier) -- the narrow-band case, where a
+//             panel never has more trailing tiles than a cluster has CTAs.
+template <bool CL> struct CholSync {
+    __device__ __forceinline__ static void sync() {
+        if (CL) cg::this_cluster().sync(); else cg::this_grid().sync();
+    }
+};
+
+template <bool CL>
 __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ double ysm[];              // [n] right-hand side of the y-CTA (when it fits)
     __shared__ double Ld[CH_NB][CH_NB + 1];      // factored diagonal block, Ld[r][c] = L(r,c)
     __shared__ double invd[CH_NB];
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
 
     for (size_t j = gtid; j < (size_t)n; j += gthreads) S[j * ld + j] += a.lambda;
     if (ycta) for (int j = tid; j < n; j += CH_THREADS) yv[j] = a.bp[j] + a.bs[j];
-    grid.sync();
+    CholSync<CL>::sync();
 
     bool failed = false;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
         }
         __syncthreads();
         PROF_TICK(1);
-        grid.sync();
+        CholSync<CL>::sync();
         PROF_TICK(2);
         // the factored diagonal block goes back only now: during phase A other CTAs were still reading the original
         if (ycta) {
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
         }
         __syncthreads();
         PROF_TICK(4);
-        grid.sync();
+        CholSync<CL>::sync();
         PROF_TICK(5);
     }
     if (failed) {
@@ -313,6 +323,279 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
     }
     __syncthreads();
     for (int j = tid; j < n; j += CH_THREADS) a.x[j] = yv[j];
+    PROF_TICK(6);
+    if (a.prof && tid == 0) for (int i = 0; i < 8; i++) a.prof[i] = pc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrow-band variant: ONE thread-block cluster, the active window of the factorisation lives in shared memory.
+//
+// A bundle-adjustment window has local covisibility, so a panel of 32 columns reaches only R <= maxr rows (a few hundred).
+// The matrix is cut into 32-wide block columns; block column c is owned by cluster CTA (c mod NC) and sits in that CTA's
+// shared memory from the moment the CTA takes it (loaded from the band buffer, + lambda) until it is factored:
+//   owner of c : potrf of the diagonal block (whole CTA), TRSM of the rows below (thread = row, registers), L written back
+//                to the band buffer (the final result, also how the other CTAs get it), forward substitution of y rides along;
+//   cluster barrier (hardware, a few hundred cycles);
+//   every CTA whose block column is reached by panel c stages the rows of L it needs from L2 and applies the rank-32
+//   update to its own block in shared memory -- no global read-modify-write anywhere; the owner meanwhile takes block c+NC.
+// NC * 32 >= maxr guarantees a CTA is done with block c before panel c+NC's first update arrives. The critical path per
+// panel is update(own block) + potrf + TRSM + barrier; the other updates overlap with it. CTA 0 runs the backward
+// substitution at the end.
+#define CB_THREADS 512
+#define CB_WARPS (CB_THREADS / 32)
+#define CB_LD 34             // shared-memory row stride (doubles) of a block column: 16-byte aligned rows, 4-bank row skew
+#define CB_MAXR 384          // rows (diagonal block included) a panel may reach
+#define CB_PAD 4
+
+__device__ __forceinline__ size_t chol_band_smem_doubles(int maxr) { return 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
+
+// 32x32 Cholesky in shared memory by the whole CTA. Per 8 columns: warp 0 factors the 32x8 panel in registers
+// (lane = row; the rows below the 8x8 block are solved by the same instruction stream), then all threads apply the rank-8
+// update to the remaining lower triangle, one element per thread.
+__device__ __forceinline__ bool cta_potrf32(double (*Ld)[CH_NB + 1], double *invd, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    bool ok = true;
+    for (int kb = 0; kb < CH_NB; kb += 8) {
+        if (warp == 0) {
+            double a[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = Ld[lane][kb + j];
+            double myrs = 1.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double dkk = __shfl_sync(0xffffffffu, a[k], kb + k);
+                if (!(dkk > 0.0)) ok = false;
+                const double rs = rsqrt(dkk);
+                if (lane == kb + k) { a[k] = dkk * rs; myrs = rs; }
+                else if (lane > kb + k) a[k] *= rs;
+#pragma unroll
+                for (int j = k + 1; j < 8; j++) {
+                    const double ljk = __shfl_sync(0xffffffffu, a[k], kb + j);
+                    if (lane >= kb + j) a[j] -= a[k] * ljk;
+                }
+            }
+            if (lane >= kb) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (kb + j <= lane) Ld[lane][kb + j] = a[j];
+                if (lane < kb + 8) invd[lane] = myrs;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
+            const int i = e >> 5, j = e & 31;
+            if (j >= kb + 8 && i >= j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) s += Ld[i][kb + k] * Ld[j][kb + k];
+                Ld[i][j] -= s;
+            }
+        }
+        __syncthreads();
+    }
+    return ok;   // meaningful in warp 0
+}
+
+__global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int NC = (int)cl.num_blocks(), o = (int)cl.block_rank();
+    extern __shared__ double cb_sm[];
+    double *Cb = cb_sm;                                        // own block column [maxr + pad][CB_LD]
+    double *Ls = cb_sm + (size_t)(maxr + CB_PAD) * CB_LD;      // staged rows of the panel being applied
+    __shared__ double Ld[CH_NB][CH_NB + 1];
+    __shared__ double invd[CH_NB], yc[CH_NB];
+    __shared__ int s_fail;
+    double *S = a.S;
+    const int n = a.n, ld = a.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = (n + CH_NB - 1) / CH_NB;
+
+    if (tid == 0) s_fail = 0;
+    for (int j = o * CB_THREADS + tid; j < n; j += NC * CB_THREADS) a.y[j] = a.bp[j] + a.bs[j];
+
+    // block column c of (S + lambda I) -> Cb (rows p0 .. rend, lower part; the strict upper part of the diagonal block = 0)
+    auto load_block = [&](int c) {
+        const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+        const int R = min(n - 1, a.col_end[p0 + nb - 1]) - p0 + 1;
+        for (int j = warp; j < CH_NB; j += CB_WARPS) {
+            const double *col = S + (size_t)(p0 + j) * ld + p0;
+#pragma unroll 4
+            for (int i = lane; i < R; i += 32) {
+                double v = 0.0;
+                if (j < nb && i >= j) { v = __ldcg(col + i); if (i == j) v += a.lambda; }
+                Cb[i * CB_LD + j] = v;
+            }
+        }
+    };
+    int cur = o;
+    if (cur < P) load_block(cur);
+    cl.sync();
+
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+    if (a.prof) t0 = clock64();
+    bool failed = false;
+    for (int c = 0; c < P; c++) {
+        const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);
+        const int R = rend - p0 + 1;
+        const bool owner = (c == cur);
+        if (owner) {
+            double yreg = 0.0;
+            if (warp == CB_WARPS - 1 && lane < nb) yreg = __ldcg(a.y + p0 + lane);      // in flight during the potrf
+            for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
+                const int i = e >> 5, j = e & 31;
+                Ld[i][j] = (i < nb && j < nb) ? ((j <= i) ? Cb[i * CB_LD + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            const bool ok = cta_potrf32(Ld, invd, tid);
+            if (warp == 0 && !ok && lane < NC) *cl.map_shared_rank(&s_fail, lane) = 1;
+            PROF_TICK(0);
+            if (warp == CB_WARPS - 1) {
+                // forward substitution rides along: y_p = L11^{-1} y_p
+                double v = yreg;
+                for (int k = 0; k < nb; k++) {
+                    const double yk = __shfl_sync(0xffffffffu, v, k) * invd[k];
+                    if (lane == k) v = yk;
+                    else if (lane > k) v -= Ld[lane][k] * yk;
+                }
+                yc[lane] = (lane < nb) ? v : 0.0;
+                if (lane < nb) __stcg(a.y + p0 + lane, v);
+            }
+            // TRSM  X L11^T = A21 : thread = row, the whole row in registers
+            const int i = CH_NB + tid;
+            const bool act = i < R;
+            double x[CH_NB];
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < CH_NB; k += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(Cb + i * CB_LD + k);
+                    x[k] = v.x; x[k + 1] = v.y;
+                }
+#pragma unroll
+                for (int k = 0; k < CH_NB; k++) {
+                    const double xk = x[k] * invd[k];
+                    x[k] = xk;
+#pragma unroll
+                    for (int j = k + 1; j < CH_NB; j++) x[j] -= xk * Ld[j][k];
+                }
+#pragma unroll
+                for (int k = 0; k < CH_NB; k++) if (k < nb) __stcg(S + (size_t)(p0 + k) * ld + p0 + i, x[k]);
+            }
+            PROF_TICK(1);
+            // factored diagonal block back to the band buffer
+            for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
+                const int i2 = e & 31, j = e >> 5;
+                if (i2 < nb && j <= i2) __stcg(S + (size_t)(p0 + j) * ld + p0 + i2, Ld[i2][j]);
+            }
+            if (tid < nb) a.dinv[p0 + tid] = invd[tid];
+            __syncthreads();                                   // yc complete
+            if (act) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < CH_NB; k++) s += x[k] * yc[k];
+                __stcg(a.y + p0 + i, __ldcg(a.y + p0 + i) - s);
+            }
+            PROF_TICK(2);
+        }
+        cl.sync();
+        PROF_TICK(3);
+        if (s_fail) { failed = true; break; }
+        if (owner) {
+            cur += NC;
+            if (cur < P) load_block(cur);
+            __syncthreads();
+            PROF_TICK(5);
+        } else if (cur < P && CH_NB * cur <= rend) {
+            // rows 32 cur .. rend of panel c -> Ls[i][k]; the first 32 staged rows are also the column operand
+            const int r0 = CH_NB * cur, nr = rend - r0 + 1;
+            for (int k = warp; k < CH_NB; k += CB_WARPS) {
+                const double *col = S + (size_t)(p0 + k) * ld + r0;
+#pragma unroll 4
+                for (int i = lane; i < nr; i += 32) Ls[i * CB_LD + k] = __ldcg(col + i);
+            }
+            __syncthreads();
+            // Cb[i][j] -= sum_k Ls[i][k] Ls[j][k]; thread tile: rows rg + 64 u, columns cg + 8 v (conflict-free rows)
+            const int cgc = tid & 7, rg = tid >> 3;
+            for (int rb = 0; rb < nr; rb += 256) {
+                if (rb + rg >= nr) break;
+                double acc[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+                int ri[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) ri[u] = min(rb + rg + 64 * u, nr - 1);
+#pragma unroll 4
+                for (int k = 0; k < CH_NB; k += 2) {
+                    double2 av[4], bv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) av[u] = *reinterpret_cast<const double2 *>(Ls + ri[u] * CB_LD + k);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) bv[v] = *reinterpret_cast<const double2 *>(Ls + (cgc + 8 * v) * CB_LD + k);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int v = 0; v < 4; v++) acc[u][v] += av[u].x * bv[v].x + av[u].y * bv[v].y;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (rb + rg + 64 * u >= nr) continue;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Cb[ri[u] * CB_LD + cgc + 8 * v] -= acc[u][v];
+                }
+            }
+            __syncthreads();
+            PROF_TICK(4);
+        }
+    }
+    if (failed) {
+        if (o == 0 && tid == 0) *a.fail = 1;
+        return;
+    }
+    if (o != 0) return;
+    // ---- backward substitution L^T x = y (CTA 0), right-hand side in shared memory when it fits
+    double *yv = cb_sm;
+    const bool ysm = (size_t)n <= chol_band_smem_doubles(maxr);
+    if (!ysm) yv = a.y;
+    __syncthreads();
+    if (ysm) for (int j = tid; j < n; j += CB_THREADS) yv[j] = __ldcg(a.y + j);
+    double *part = yc;
+    for (int c = P - 1; c >= 0; c--) {
+        const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+        const int rbase = p0 + nb;
+        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);
+        __syncthreads();
+        if (warp == CB_WARPS - 1) {
+            for (int j = 0; j < CH_NB; j++)
+                Ld[lane][j] = (lane < nb && j < nb && j <= lane) ? __ldcg(S + (size_t)(p0 + j) * ld + p0 + lane) : 0.0;
+            invd[lane] = (lane < nb) ? __ldcg(a.dinv + p0 + lane) : 1.0;
+        }
+#pragma unroll
+        for (int q = 0; q < CH_NB / CB_WARPS; q++) {
+            const int j = warp + q * CB_WARPS;
+            double sacc = 0.0;
+            if (j < nb) {
+                const double *col = S + (size_t)(p0 + j) * ld;
+#pragma unroll 4
+                for (int i = rbase + lane; i <= rend; i += 32) sacc += __ldcg(col + i) * yv[i];
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+            if (lane == 0) part[j] = sacc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double v = (lane < nb) ? yv[p0 + lane] - part[lane] : 0.0;
+            for (int i = nb - 1; i >= 0; i--) {
+                const double xi = __shfl_sync(0xffffffffu, v, i) * invd[i];
+                if (lane == i) v = xi;
+                else if (lane < i) v -= Ld[i][lane] * xi;
+            }
+            if (lane < nb) yv[p0 + lane] = v;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += CB_THREADS) a.x[j] = yv[j];
     PROF_TICK(6);
     if (a.prof && tid == 0) for (int i = 0; i < 8; i++) a.prof[i] = pc[i];
 }
