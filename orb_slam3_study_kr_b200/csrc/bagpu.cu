@@ -631,7 +631,28 @@ size_t chol_dyn_smem(int n) { return n <= CH_MAX_SMEM_N ? sizeof(double) * (size
 //  * otherwise chol_solve_kernel: one CTA per trailing tile (or TRSM row pass) plus the CTA that owns the right-hand side;
 //    up to CH_CLUSTER_MAX CTAs as one cluster (hardware barrier), beyond that a cooperative launch.
 #define CH_CLUSTER_MAX 16
-size_t chol_band_smem(int maxr) { return sizeof(double) * 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
+size_t chol_band_smem_min(int maxr) { return sizeof(double) * 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
+size_t chol_band_smem_cap() {
+    static size_t cap = 0;
+    if (!cap) {
+        cudaFuncAttributes fa;
+        cap = 200 * 1024;
+        if (cudaFuncGetAttributes(&fa, chol_band_kernel) == cudaSuccess) cap = 232448 - fa.sharedSizeBytes - 1024;
+    }
+    return cap;
+}
+// dynamic shared memory of the band kernel: the two block-column buffers of the factorisation, or -- when it still fits --
+// the right-hand side plus two prefetched panels for the backward substitution, whichever is larger
+size_t chol_band_smem(int n, int maxr) {
+    const size_t cap = chol_band_smem_cap();
+    const size_t need = chol_band_smem_min(maxr);
+    const size_t bs = (size_t)((maxr + 1) | 1);
+    const size_t back = sizeof(double) * ((size_t)n + 2 * CH_NB * bs);
+    const size_t ysm = sizeof(double) * (size_t)n;
+    if (back <= cap) return std::max(need, back);
+    if (ysm <= cap) return std::max(need, ysm);
+    return need;
+}
 
 int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out) {
     static bool attr_set = false;
@@ -639,14 +660,14 @@ int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *max
         CK(cudaFuncSetAttribute(chol_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
         CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
         CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_band_smem(CB_MAXR)));
+        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_band_smem_cap()));
         CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
     static const bool no_band = getenv("BAGPU_NO_BAND") != nullptr;
     const int maxr = max_below + CH_NB;
     if (maxr <= CB_MAXR && !no_band) {
-        int nc = 1;
+        int nc = 2;
         while (nc * CH_NB < maxr) nc *= 2;
         *grid_out = nc; *maxr_out = maxr;
         return BAGPU_OK;
@@ -670,8 +691,8 @@ int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr) {
     cfg.gridDim = dim3(grid); cfg.stream = ctx->stream; cfg.attrs = at; cfg.numAttrs = 1;
     if (maxr > 0) {
         cfg.blockDim = dim3(CB_THREADS);
-        cfg.dynamicSmemBytes = chol_band_smem(maxr);
-        CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr));
+        cfg.dynamicSmemBytes = chol_band_smem(a.n, maxr);
+        CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr, (int)(cfg.dynamicSmemBytes / sizeof(double))));
         return BAGPU_OK;
     }
     if (grid <= CH_CLUSTER_MAX && !no_cluster) {
@@ -1112,7 +1133,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     DevBuf dS, db, dz, dx, dy, dc, df, dd;
     CK(dd.ensure(8 * (size_t)n));
     CK(dS.ensure(8 * s_elems)); CK(db.ensure(8 * (size_t)n)); CK(dz.ensure(8 * (size_t)n)); CK(dx.ensure(8 * (size_t)n));
-    CK(dy.ensure(8 * (size_t)n)); CK(dc.ensure(4 * (size_t)n)); CK(df.ensure(16 + 64));
+    CK(dy.ensure(8 * (size_t)n)); CK(dc.ensure(4 * (size_t)n)); CK(df.ensure(16 + 256));
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(dS.p, hS.data(), 8 * s_elems, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(db.p, b, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1131,10 +1152,19 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaStreamSynchronize(st));
     if (fail_out) *fail_out = hf;
     if (getenv("BAGPU_DEBUG")) {
-        long long hp[8];
-        cudaMemcpy(hp, (char *)df.p + 16, 64, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d maxr=%d: [0]potrf %lld [1]trsm %lld [2]sync1|wb+y %lld [3]wb+y|sync %lld [4]update %lld [5]sync2|take %lld [6]backward %lld\n",
-                n, ld, tgrid, tmaxr, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+        long long hp[24];
+        cudaMemcpy(hp, (char *)df.p + 16, 192, cudaMemcpyDeviceToHost);
+        if (tmaxr > 0 && hf) fprintf(stderr, "[bagpu] band chol FAILED at panel %lld (n=%d maxr=%d grid=%d)\n", hp[23] - 1, n, tmaxr, tgrid);
+        else if (tmaxr > 0) {
+            fprintf(stderr, "[bagpu] band chol n=%d ld=%d grid=%d maxr=%d (CTA 0 cycles)\n  owner: trsm %lld wb+y %lld barrier %lld take %lld endsync %lld\n"
+                    "  next : flagwait %lld diagupd %lld ldbuild %lld potrf %lld clwait %lld endsync %lld\n  other: barrier %lld stage %lld update %lld endsync %lld\n"
+                    "  final sync %lld | backward: topsync %lld prefetch+wait %lld dots %lld chain %lld | owner top %lld trsm-loop %lld | potrf chains %lld\n",
+                    n, ld, tgrid, tmaxr, hp[0], hp[1], hp[2], hp[3], hp[13], hp[4], hp[5], hp[6], hp[7], hp[8], hp[9], hp[10], hp[11], hp[12], hp[14],
+                    hp[15], hp[16], hp[17], hp[18], hp[19], hp[20], hp[21], hp[22]);
+        } else {
+            fprintf(stderr, "[bagpu] chol cycles n=%d ld=%d grid=%d: potrf %lld trsm %lld sync1 %lld wb+y %lld update %lld sync2 %lld backward %lld\n",
+                    n, ld, tgrid, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+        }
     }
     dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
     return BAGPU_OK;

@@ -332,90 +332,181 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
 //
 // A bundle-adjustment window has local covisibility, so a panel of 32 columns reaches only R <= maxr rows (a few hundred).
 // The matrix is cut into 32-wide block columns; block column c is owned by cluster CTA (c mod NC) and sits in that CTA's
-// shared memory from the moment the CTA takes it (loaded from the band buffer, + lambda) until it is factored:
-//   owner of c : potrf of the diagonal block (whole CTA), TRSM of the rows below (thread = row, registers), L written back
-//                to the band buffer (the final result, also how the other CTAs get it), forward substitution of y rides along;
-//   cluster barrier (hardware, a few hundred cycles);
-//   every CTA whose block column is reached by panel c stages the rows of L it needs from L2 and applies the rank-32
-//   update to its own block in shared memory -- no global read-modify-write anywhere; the owner meanwhile takes block c+NC.
-// NC * 32 >= maxr guarantees a CTA is done with block c before panel c+NC's first update arrives. The critical path per
-// panel is update(own block) + potrf + TRSM + barrier; the other updates overlap with it. CTA 0 runs the backward
-// substitution at the end.
+// shared memory from the moment the CTA takes it (loaded from the band buffer, + lambda) until it is factored. There is
+// no global read-modify-write anywhere. Step c of the pipeline (B_c = hardware cluster barrier "panel c is in L2"):
+//   owner(c)      TRSM of the rows below the (already factored) diagonal block, thread = row, registers. Warp 0 holds
+//                 the 32 rows that form the NEXT diagonal block: it pushes them straight into owner(c+1)'s shared memory
+//                 (DSMEM) and raises a flag. All rows go to the band buffer (the result, and how the others get them);
+//                 the forward substitution of y rides along. Arrive/wait B_c, then take block column c+NC.
+//   owner(c+1)    warps 0-3: wait for the flag, subtract the pushed rows from their diagonal block and factor it (potrf),
+//                 i.e. the next panel's critical path starts before panel c is even complete;
+//                 warps 4-15: wait B_c, stage the remaining rows from L2, rank-32 update of the rows under the diagonal.
+//   other CTAs    wait B_c, stage the rows that reach their block column, rank-32 update of the whole block.
+// NC * 32 >= maxr guarantees a CTA is done with block c before panel c+NC's first update arrives. CTA 0 runs the backward
+// substitution at the end with the panels double-buffered into shared memory by cp.async.
 #define CB_THREADS 512
 #define CB_WARPS (CB_THREADS / 32)
+#define CB_PG 128            // threads of the potrf group (warps 0-3)
 #define CB_LD 34             // shared-memory row stride (doubles) of a block column: 16-byte aligned rows, 4-bank row skew
-#define CB_MAXR 384          // rows (diagonal block included) a panel may reach
+#define CB_MAXR 352          // rows (diagonal block included) a panel may reach
 #define CB_PAD 4
+#define CB_MAXP 512          // panels whose extent is cached in shared memory
 
-__device__ __forceinline__ size_t chol_band_smem_doubles(int maxr) { return 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
+__device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_release_cluster(int *p, int v) { asm volatile("st.release.cluster.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_cluster(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cluster.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 
-// 32x32 Cholesky in shared memory by the whole CTA. Per 8 columns: warp 0 factors the 32x8 panel in registers
-// (lane = row; the rows below the 8x8 block are solved by the same instruction stream), then all threads apply the rank-8
-// update to the remaining lower triangle, one element per thread.
-__device__ __forceinline__ bool cta_potrf32(double (*Ld)[CH_NB + 1], double *invd, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
+// 32x32 Cholesky in shared memory by a group of NT threads (whole warps, named barrier 1), 8 columns at a time:
+//  * warp 0 ("chain"): lane = row, 8 pivots; pivot and column entries travel by shuffle (FP64 instruction issue, not
+//    shuffle latency, is the scarce resource: ~5 cycles per DP instruction per warp);
+//  * right after, the whole group updates only the NEXT 8 columns (what the next chain needs);
+//  * the update of the columns further right is deferred: warps 1.. apply it while warp 0 already runs the next chain.
+// tri[e] = (row << 8 | col) enumerates a lower triangle row by row (a smaller triangle is a prefix). Returns ok in warp 0.
+template <int NT>
+__device__ __forceinline__ bool group_potrf32(double (*Ld)[CH_NB + 1], double *invd, const unsigned short *tri, int t, long long *chain_cyc) {
+    const int lane = t & 31, warp = t >> 5;
     bool ok = true;
     for (int kb = 0; kb < CH_NB; kb += 8) {
+        const long long tc0 = chain_cyc ? clock64() : 0;
         if (warp == 0) {
-            double a[8];
+            // lane = row (all 32 rows: the rows below the 8x8 block are solved by the same instruction stream); the pivot
+            // and the column entries travel by shuffle. DP instructions are what costs here, so nothing is replicated.
+            double a8[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) a[j] = Ld[lane][kb + j];
+            for (int q = 0; q < 8; q++) a8[q] = Ld[lane][kb + q];
             double myrs = 1.0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const double dkk = __shfl_sync(0xffffffffu, a[k], kb + k);
+                const double dkk = __shfl_sync(0xffffffffu, a8[k], kb + k);
                 if (!(dkk > 0.0)) ok = false;
                 const double rs = rsqrt(dkk);
-                if (lane == kb + k) { a[k] = dkk * rs; myrs = rs; }
-                else if (lane > kb + k) a[k] *= rs;
+                if (lane == kb + k) { a8[k] = dkk * rs; myrs = rs; }
+                else a8[k] *= rs;
 #pragma unroll
-                for (int j = k + 1; j < 8; j++) {
-                    const double ljk = __shfl_sync(0xffffffffu, a[k], kb + j);
-                    if (lane >= kb + j) a[j] -= a[k] * ljk;
+                for (int q = k + 1; q < 8; q++) {
+                    const double lqk = __shfl_sync(0xffffffffu, a8[k], kb + q);
+                    a8[q] -= a8[k] * lqk;
                 }
             }
             if (lane >= kb) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) if (kb + j <= lane) Ld[lane][kb + j] = a[j];
+                for (int q = 0; q < 8; q++) if (kb + q <= lane) Ld[lane][kb + q] = a8[q];
                 if (lane < kb + 8) invd[lane] = myrs;
             }
-        }
-        __syncthreads();
-        for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
-            const int i = e >> 5, j = e & 31;
-            if (j >= kb + 8 && i >= j) {
-                double s = 0.0;
+            if (chain_cyc) *chain_cyc += clock64() - tc0;
+        } else if (kb >= 8 && kb + 8 < CH_NB) {
+            // deferred: columns >= kb + 8 get the rank-8 update of the PREVIOUS sub-block (kb - 8)
+            const int base = kb + 8, m = CH_NB - base, cnt = m * (m + 1) / 2, pk = kb - 8;
+            for (int e = t - 32; e < cnt; e += NT - 32) {
+                const int rc = tri[e], i = base + (rc >> 8), jj = base + (rc & 255);
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) s += Ld[i][kb + k] * Ld[j][kb + k];
-                Ld[i][j] -= s;
+                for (int k = 0; k < 8; k += 2) { s0 += Ld[i][pk + k] * Ld[jj][pk + k]; s1 += Ld[i][pk + k + 1] * Ld[jj][pk + k + 1]; }
+                Ld[i][jj] -= s0 + s1;
             }
         }
-        __syncthreads();
+        bar_named(1, NT);
+        if (kb + 8 < CH_NB) {
+            // the next 8 columns (rows >= column) get this sub-block's update now
+            const int base = kb + 8, cnt = (CH_NB - base) * 8;
+            for (int e = t; e < cnt; e += NT) {
+                const int i = base + (e >> 3), jj = base + (e & 7);
+                if (i >= jj) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2) { s0 += Ld[i][kb + k] * Ld[jj][kb + k]; s1 += Ld[i][kb + k + 1] * Ld[jj][kb + k + 1]; }
+                    Ld[i][jj] -= s0 + s1;
+                }
+            }
+            bar_named(1, NT);
+        }
     }
-    return ok;   // meaningful in warp 0
+    return ok;
 }
 
-__global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr) {
+// Cb[i][j] -= sum_k Lr[i][k] Lc[j][k] for rows row_lo <= i < nr, all 32 columns j, by NT threads (t = 0..NT-1).
+// Thread tile: U rows rg + (NT/8) u, 4 columns cg + 8 v, so neighbouring lanes touch neighbouring rows (conflict-free
+// LDS.128).
+template <int NT, int U>
+__device__ __forceinline__ void rank32_update(double *Cb, const double *Lr, const double *Lc, int row_lo, int nr, int t) {
+    constexpr int RP = NT / 8;
+    const int cgc = t & 7, rg = t >> 3;
+    for (int rb = row_lo; rb + rg < nr; rb += U * RP) {
+        double acc[U][4];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+        int ri[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) ri[u] = min(rb + rg + RP * u, nr - 1);
+#pragma unroll 4
+        for (int k = 0; k < CH_NB; k += 2) {
+            double2 av[U], bv[4];
+#pragma unroll
+            for (int u = 0; u < U; u++) av[u] = *reinterpret_cast<const double2 *>(Lr + ri[u] * CB_LD + k);
+#pragma unroll
+            for (int v = 0; v < 4; v++) bv[v] = *reinterpret_cast<const double2 *>(Lc + (cgc + 8 * v) * CB_LD + k);
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] += av[u].x * bv[v].x + av[u].y * bv[v].y;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rb + rg + RP * u >= nr) continue;
+#pragma unroll
+            for (int v = 0; v < 4; v++) Cb[ri[u] * CB_LD + cgc + 8 * v] -= acc[u][v];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr, int dyn_doubles) {
     cg::cluster_group cl = cg::this_cluster();
     const int NC = (int)cl.num_blocks(), o = (int)cl.block_rank();
     extern __shared__ double cb_sm[];
     double *Cb = cb_sm;                                        // own block column [maxr + pad][CB_LD]
     double *Ls = cb_sm + (size_t)(maxr + CB_PAD) * CB_LD;      // staged rows of the panel being applied
     __shared__ double Ld[CH_NB][CH_NB + 1];
+    __shared__ __align__(16) double Lt[CH_NB * CB_LD];         // rows of the previous panel that make up my diagonal block
+    __shared__ __align__(16) double LdT[CH_NB][CH_NB];        // LdT[m][j] = L11(j, m), j > m: what the TRSM streams
     __shared__ double invd[CH_NB], yc[CH_NB];
-    __shared__ int s_fail;
+    __shared__ unsigned short tri[CH_NB * (CH_NB + 1) / 2];
+    __shared__ int s_fail, s_flag;
+    __shared__ int s_rend[CB_MAXP];                            // last row of every panel (col_end of its last column)
     double *S = a.S;
     const int n = a.n, ld = a.ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = (n + CH_NB - 1) / CH_NB;
+    for (int c = tid; c < min(P, CB_MAXP); c += CB_THREADS) s_rend[c] = min(n - 1, a.col_end[min(n, (c + 1) * CH_NB) - 1]);
+    auto rend_of = [&](int c) { return c < CB_MAXP ? s_rend[c] : min(n - 1, a.col_end[min(n, (c + 1) * CH_NB) - 1]); };
+    for (int e = tid; e < CH_NB * (CH_NB + 1) / 2; e += CB_THREADS) {
+        int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+        while ((r + 1) * (r + 2) / 2 <= e) r++;
+        while (r * (r + 1) / 2 > e) r--;
+        tri[e] = (unsigned short)((r << 8) | (e - r * (r + 1) / 2));
+    }
 
-    if (tid == 0) s_fail = 0;
+    long long pc[24], t0 = 0, t1 = 0;
+#pragma unroll
+    for (int q = 0; q < 24; q++) pc[q] = 0;
+#define BT(i) do { if (a.prof) { t1 = clock64(); pc[i] += t1 - t0; t0 = t1; } } while (0)
+    if (tid == 0) { s_fail = 0; s_flag = 0; }
     for (int j = o * CB_THREADS + tid; j < n; j += NC * CB_THREADS) a.y[j] = a.bp[j] + a.bs[j];
 
     // block column c of (S + lambda I) -> Cb (rows p0 .. rend, lower part; the strict upper part of the diagonal block = 0)
     auto load_block = [&](int c) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
-        const int R = min(n - 1, a.col_end[p0 + nb - 1]) - p0 + 1;
+        const int R = rend_of(c) - p0 + 1;
         for (int j = warp; j < CH_NB; j += CB_WARPS) {
             const double *col = S + (size_t)(p0 + j) * ld + p0;
 #pragma unroll 4
@@ -426,176 +517,273 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
             }
         }
     };
+    // Ld <- diagonal block of Cb (minus Lt Lt^T when the previous panel reaches it), identity beyond nb; potrf; flag a failure
+    auto factor_diag = [&](int c, bool sub) {                  // potrf group only, t = tid < CB_PG
+        const int nb = min(CH_NB, n - c * CH_NB);
+        // Ld <- lower part of (diagonal block - Lt Lt^T), identity beyond nb
+        for (int e = tid; e < CH_NB * (CH_NB + 1) / 2; e += CB_PG) {
+            const int rc = tri[e], i = rc >> 8, j = rc & 255;
+            double v = (i == j) ? 1.0 : 0.0;
+            if (i < nb) {
+                v = Cb[i * CB_LD + j];
+                if (sub) {
+                    double s0 = 0.0, s1 = 0.0;
+                    const double2 *li = reinterpret_cast<const double2 *>(Lt + i * CB_LD), *lj = reinterpret_cast<const double2 *>(Lt + j * CB_LD);
+#pragma unroll 4
+                    for (int k = 0; k < CH_NB / 2; k++) { const double2 p = li[k], q = lj[k]; s0 += p.x * q.x; s1 += p.y * q.y; }
+                    v -= s0 + s1;
+                }
+            }
+            Ld[i][j] = v;
+        }
+        bar_named(1, CB_PG);
+        BT(5);
+        const bool ok = group_potrf32<CB_PG>(Ld, invd, tri, tid, a.prof ? &pc[22] : nullptr);
+        BT(6);
+        if (warp == 0 && !ok && lane < NC) atomicCAS(cl.map_shared_rank(&s_fail, lane), 0, c + 1);   // the first failure wins
+        for (int e = tid; e < CH_NB * CH_NB; e += CB_PG) {
+            const int m = e >> 5, j = e & 31;
+            LdT[m][j] = (j > m) ? Ld[j][m] : 0.0;
+        }
+    };
+
+    __syncthreads();                                           // s_rend, tri
     int cur = o;
     if (cur < P) load_block(cur);
     cl.sync();
+    if (o == 0 && tid < CB_PG) factor_diag(0, false);
+    __syncthreads();
 
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
     if (a.prof) t0 = clock64();
     bool failed = false;
     for (int c = 0; c < P; c++) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
-        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);
+        const int rend = rend_of(c);
         const int R = rend - p0 + 1;
-        const bool owner = (c == cur);
+        const bool owner = (c == cur), nextowner = (c + 1 == cur && cur < P);
         if (owner) {
-            double yreg = 0.0;
-            if (warp == CB_WARPS - 1 && lane < nb) yreg = __ldcg(a.y + p0 + lane);      // in flight during the potrf
-            for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
-                const int i = e >> 5, j = e & 31;
-                Ld[i][j] = (i < nb && j < nb) ? ((j <= i) ? Cb[i * CB_LD + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
-            }
-            __syncthreads();
-            const bool ok = cta_potrf32(Ld, invd, tid);
-            if (warp == 0 && !ok && lane < NC) *cl.map_shared_rank(&s_fail, lane) = 1;
-            PROF_TICK(0);
+            BT(20);
             if (warp == CB_WARPS - 1) {
                 // forward substitution rides along: y_p = L11^{-1} y_p
-                double v = yreg;
-                for (int k = 0; k < nb; k++) {
-                    const double yk = __shfl_sync(0xffffffffu, v, k) * invd[k];
-                    if (lane == k) v = yk;
-                    else if (lane > k) v -= Ld[lane][k] * yk;
+                const double di = invd[lane];
+                double v = (lane < nb) ? __ldcg(a.y + p0 + lane) * di : 0.0;
+#pragma unroll
+                for (int k = 0; k < CH_NB - 1; k++) {
+                    const double yk = __shfl_sync(0xffffffffu, v, k);
+                    const double l = (lane > k && lane < nb) ? Ld[lane][k] * di : 0.0;
+                    v -= l * yk;
                 }
                 yc[lane] = (lane < nb) ? v : 0.0;
                 if (lane < nb) __stcg(a.y + p0 + lane, v);
             }
             // TRSM  X L11^T = A21 : thread = row, the whole row in registers
-            const int i = CH_NB + tid;
-            const bool act = i < R;
-            double x[CH_NB];
-            if (act) {
+            // warp 0 holds the rows of the next diagonal block (the critical path); the others skip warps 4, 8, 12 so that
+            // warp 0 has its scheduler to itself
+            const int rw = (warp == 0) ? 0 : ((warp & 3) ? warp - (warp >> 2) : 12 + (warp >> 2));   // 0 | 1..9 | 13..15 spare
+            const int i = CH_NB + 32 * rw + lane;
+            const bool act = (warp != CB_WARPS - 1) && i < R;
+            const bool push = (warp == 0) && (c + 1 < P) && (R > CH_NB);
+            const int r = 32 * rw + lane;                      // row slot; solved values go to Xs[k][r] (the staging buffer is idle)
+            const int XR = (R - CH_NB + 31) & ~31;
+            double *Xs = Ls;
+            if (act || push) {
+                double *rt = push ? cl.map_shared_rank(Lt, (o + 1) % NC) + lane * CB_LD : nullptr;
+#pragma unroll 1
+                for (int kb = 0; kb < CH_NB; kb += 8) {
+                    double xr[8];
 #pragma unroll
-                for (int k = 0; k < CH_NB; k += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(Cb + i * CB_LD + k);
-                    x[k] = v.x; x[k + 1] = v.y;
+                    for (int q = 0; q < 8; q += 2) {
+                        double2 v = make_double2(0.0, 0.0);
+                        if (act) v = *reinterpret_cast<const double2 *>(Cb + i * CB_LD + kb + q);
+                        xr[q] = v.x; xr[q + 1] = v.y;
+                    }
+#pragma unroll 2
+                    for (int m = 0; m < kb; m++) {
+                        const double xm = Xs[m * XR + r];
+                        const double2 *lt = reinterpret_cast<const double2 *>(&LdT[m][kb]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { const double2 l = lt[q]; xr[2 * q] -= xm * l.x; xr[2 * q + 1] -= xm * l.y; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const double xk = xr[k] * invd[kb + k];
+                        xr[k] = xk;
+#pragma unroll
+                        for (int q = k + 1; q < 8; q++) xr[q] -= xk * LdT[kb + k][kb + q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) Xs[(kb + q) * XR + r] = xr[q];
+                    if (push) {
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(rt + kb + q) = make_double2(xr[q], xr[q + 1]);
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (kb + q < nb) __stcg(S + (size_t)(p0 + kb + q) * ld + p0 + i, xr[q]);
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < CH_NB; k++) {
-                    const double xk = x[k] * invd[k];
-                    x[k] = xk;
-#pragma unroll
-                    for (int j = k + 1; j < CH_NB; j++) x[j] -= xk * Ld[j][k];
+                BT(21);
+                if (push) {
+                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) st_release_cluster(cl.map_shared_rank(&s_flag, (o + 1) % NC), c + 1);
                 }
-#pragma unroll
-                for (int k = 0; k < CH_NB; k++) if (k < nb) __stcg(S + (size_t)(p0 + k) * ld + p0 + i, x[k]);
             }
-            PROF_TICK(1);
+            BT(0);
             // factored diagonal block back to the band buffer
             for (int e = tid; e < CH_NB * CH_NB; e += CB_THREADS) {
                 const int i2 = e & 31, j = e >> 5;
-                if (i2 < nb && j <= i2) __stcg(S + (size_t)(p0 + j) * ld + p0 + i2, Ld[i2][j]);
+                if (i2 < nb && j <= i2) __stcg(S + (size_t)(p0 + j) * ld + p0 + i2, (j == i2) ? invd[j] : Ld[i2][j]);   // diagonal: 1 / L(j,j)
             }
-            if (tid < nb) a.dinv[p0 + tid] = invd[tid];
             __syncthreads();                                   // yc complete
             if (act) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < CH_NB; k++) s += x[k] * yc[k];
-                __stcg(a.y + p0 + i, __ldcg(a.y + p0 + i) - s);
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < CH_NB; k += 2) { s0 += Xs[k * XR + r] * yc[k]; s1 += Xs[(k + 1) * XR + r] * yc[k + 1]; }
+                __stcg(a.y + p0 + i, __ldcg(a.y + p0 + i) - (s0 + s1));
             }
-            PROF_TICK(2);
-        }
-        cl.sync();
-        PROF_TICK(3);
-        if (s_fail) { failed = true; break; }
-        if (owner) {
+            BT(1);
+            cluster_arrive();
+            cluster_wait();
+            BT(2);
+            { const int sf = s_fail; if (sf != 0 && sf - 1 <= c) failed = true; }
             cur += NC;
-            if (cur < P) load_block(cur);
-            __syncthreads();
-            PROF_TICK(5);
-        } else if (cur < P && CH_NB * cur <= rend) {
-            // rows 32 cur .. rend of panel c -> Ls[i][k]; the first 32 staged rows are also the column operand
-            const int r0 = CH_NB * cur, nr = rend - r0 + 1;
-            for (int k = warp; k < CH_NB; k += CB_WARPS) {
-                const double *col = S + (size_t)(p0 + k) * ld + r0;
-#pragma unroll 4
-                for (int i = lane; i < nr; i += 32) Ls[i * CB_LD + k] = __ldcg(col + i);
-            }
-            __syncthreads();
-            // Cb[i][j] -= sum_k Ls[i][k] Ls[j][k]; thread tile: rows rg + 64 u, columns cg + 8 v (conflict-free rows)
-            const int cgc = tid & 7, rg = tid >> 3;
-            for (int rb = 0; rb < nr; rb += 256) {
-                if (rb + rg >= nr) break;
-                double acc[4][4];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-                int ri[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) ri[u] = min(rb + rg + 64 * u, nr - 1);
-#pragma unroll 4
-                for (int k = 0; k < CH_NB; k += 2) {
-                    double2 av[4], bv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) av[u] = *reinterpret_cast<const double2 *>(Ls + ri[u] * CB_LD + k);
-#pragma unroll
-                    for (int v = 0; v < 4; v++) bv[v] = *reinterpret_cast<const double2 *>(Ls + (cgc + 8 * v) * CB_LD + k);
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-#pragma unroll
-                        for (int v = 0; v < 4; v++) acc[u][v] += av[u].x * bv[v].x + av[u].y * bv[v].y;
+            if (cur < P && !failed) load_block(cur);
+            BT(3);
+        } else if (nextowner) {
+            const int r0 = CH_NB * cur, nr = rend - r0 + 1;    // rows of panel c inside my block column (may be <= 0)
+            if (tid < CB_PG) {
+                cluster_arrive();
+                if (R > CH_NB) {
+                    if (lane == 0) while (ld_acquire_cluster(&s_flag) != c + 1) { }
+                    __syncwarp();
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (rb + rg + 64 * u >= nr) continue;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) Cb[ri[u] * CB_LD + cgc + 8 * v] -= acc[u][v];
+                BT(4);
+                factor_diag(c + 1, R > CH_NB);
+                BT(7);
+                cluster_wait();
+                BT(8);
+            } else {
+                cluster_arrive();
+                cluster_wait();
+                if (nr > CH_NB) {
+                    const int t = tid - CB_PG;
+                    for (int e = t >> 5; e < CH_NB; e += (CB_THREADS - CB_PG) / 32) {
+                        const double *col = S + (size_t)(p0 + e) * ld + r0;
+#pragma unroll 4
+                        for (int i = CH_NB + lane; i < nr; i += 32) Ls[i * CB_LD + e] = __ldcg(col + i);
+                    }
+                    bar_named(2, CB_THREADS - CB_PG);
+                    rank32_update<CB_THREADS - CB_PG, 4>(Cb, Ls, Lt, CH_NB, nr, t);
                 }
             }
-            __syncthreads();
-            PROF_TICK(4);
+            { const int sf = s_fail; if (sf != 0 && sf - 1 <= c) failed = true; }
+        } else {
+            cluster_arrive();
+            cluster_wait();
+            BT(10);
+            { const int sf = s_fail; if (sf != 0 && sf - 1 <= c) failed = true; }
+            if (cur < P && CH_NB * cur <= rend && !failed) {
+                // rows 32 cur .. rend of panel c -> Ls[i][k]; the first 32 staged rows are also the column operand
+                const int r0 = CH_NB * cur, nr = rend - r0 + 1;
+                for (int k = warp; k < CH_NB; k += CB_WARPS) {
+                    const double *col = S + (size_t)(p0 + k) * ld + r0;
+#pragma unroll 4
+                    for (int i = lane; i < nr; i += 32) Ls[i * CB_LD + k] = __ldcg(col + i);
+                }
+                __syncthreads();
+                BT(11);
+                rank32_update<CB_THREADS, 4>(Cb, Ls, Ls, 0, nr, tid);
+                BT(12);
+            }
         }
+        __syncthreads();
+        BT(owner ? 13 : (nextowner ? 9 : 14));
+        if (failed) break;
     }
+    cl.sync();                                                 // nobody leaves while a remote shared-memory write may be in flight
     if (failed) {
-        if (o == 0 && tid == 0) *a.fail = 1;
+        if (o == 0 && tid == 0) { *a.fail = 1; if (a.prof) a.prof[23] = s_fail; }
         return;
     }
     if (o != 0) return;
-    // ---- backward substitution L^T x = y (CTA 0), right-hand side in shared memory when it fits
-    double *yv = cb_sm;
-    const bool ysm = (size_t)n <= chol_band_smem_doubles(maxr);
-    if (!ysm) yv = a.y;
+    BT(15);
+    // ---- backward substitution L^T x = y (CTA 0); the band buffer holds 1 / L(j,j) on the diagonal
+    const int bs = (maxr + 1) | 1;                             // odd column stride of a prefetched panel
+    const bool ysm = n <= dyn_doubles;                         // right-hand side in shared memory
+    const bool pref = n + 2 * CH_NB * bs <= dyn_doubles;       // ... and two panel buffers behind it
+    double *yv = ysm ? cb_sm : a.y;
+    double *pb = cb_sm + n;
     __syncthreads();
     if (ysm) for (int j = tid; j < n; j += CB_THREADS) yv[j] = __ldcg(a.y + j);
     double *part = yc;
+    auto prefetch = [&](int c, double *dst) {                  // columns of panel c, rows p0 .. rend -> dst[j * bs + i]
+        const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+        const int R = rend_of(c) - p0 + 1;
+        for (int j = warp; j < nb; j += CB_WARPS) {
+            const double *col = S + (size_t)(p0 + j) * ld + p0;
+            for (int i = j + lane; i < R; i += 32) cp_async8(dst + j * bs + i, col + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (pref) prefetch(P - 1, pb);
     for (int c = P - 1; c >= 0; c--) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
         const int rbase = p0 + nb;
-        const int rend = min(n - 1, a.col_end[p0 + nb - 1]);
-        __syncthreads();
-        if (warp == CB_WARPS - 1) {
+        const int rend = rend_of(c);
+        double *cbuf = pb + ((P - 1 - c) & 1) * (CH_NB * bs);
+        double dv = 1.0;
+        if (!pref && warp == 0 && lane < nb) dv = __ldcg(S + (size_t)(p0 + lane) * ld + p0 + lane);
+        __syncthreads();                                       // previous panel's x is in yv; its buffer is free
+        if (a.prof) { t1 = clock64(); pc[16] += t1 - t0; t0 = t1; }
+        if (pref) {
+            if (c > 0) { prefetch(c - 1, pb + ((P - c) & 1) * (CH_NB * bs)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        } else if (warp == CB_WARPS - 1) {
             for (int j = 0; j < CH_NB; j++)
                 Ld[lane][j] = (lane < nb && j < nb && j <= lane) ? __ldcg(S + (size_t)(p0 + j) * ld + p0 + lane) : 0.0;
-            invd[lane] = (lane < nb) ? __ldcg(a.dinv + p0 + lane) : 1.0;
         }
+        if (a.prof) { t1 = clock64(); pc[17] += t1 - t0; t0 = t1; }
+        if (pref && warp == 0 && lane < nb) dv = cbuf[lane * bs + lane];
 #pragma unroll
         for (int q = 0; q < CH_NB / CB_WARPS; q++) {
             const int j = warp + q * CB_WARPS;
             double sacc = 0.0;
             if (j < nb) {
-                const double *col = S + (size_t)(p0 + j) * ld;
+                if (pref) {
+                    const double *col = cbuf + j * bs - p0;
 #pragma unroll 4
-                for (int i = rbase + lane; i <= rend; i += 32) sacc += __ldcg(col + i) * yv[i];
+                    for (int i = rbase + lane; i <= rend; i += 32) sacc += col[i] * yv[i];
+                } else {
+                    const double *col = S + (size_t)(p0 + j) * ld;
+#pragma unroll 4
+                    for (int i = rbase + lane; i <= rend; i += 32) sacc += __ldcg(col + i) * yv[i];
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
             if (lane == 0) part[j] = sacc;
         }
         __syncthreads();
+        if (a.prof) { t1 = clock64(); pc[18] += t1 - t0; t0 = t1; }
         if (warp == 0) {
-            double v = (lane < nb) ? yv[p0 + lane] - part[lane] : 0.0;
-            for (int i = nb - 1; i >= 0; i--) {
-                const double xi = __shfl_sync(0xffffffffu, v, i) * invd[i];
-                if (lane == i) v = xi;
-                else if (lane < i) v -= Ld[i][lane] * xi;
+            // x_p = L11^{-T} v, lane = column. With column `lane` pre-scaled by 1 / L(lane,lane) the chain per row is one
+            // shuffle and one fma: x_i = v'_i - sum_{k>i} L'(k,i) x_k
+            const double *lp = pref ? cbuf + lane * bs : &Ld[0][lane];
+            const int lstep = pref ? 1 : CH_NB + 1;
+            double v = (lane < nb) ? (yv[p0 + lane] - part[lane]) * dv : 0.0;
+#pragma unroll
+            for (int i = CH_NB - 1; i >= 1; i--) {
+                const double xi = __shfl_sync(0xffffffffu, v, i);
+                const double l = (lane < i && i < nb) ? lp[i * lstep] * dv : 0.0;
+                v -= l * xi;
             }
             if (lane < nb) yv[p0 + lane] = v;
         }
+        if (a.prof) { t1 = clock64(); pc[19] += t1 - t0; t0 = t1; }
     }
     __syncthreads();
     for (int j = tid; j < n; j += CB_THREADS) a.x[j] = yv[j];
-    PROF_TICK(6);
-    if (a.prof && tid == 0) for (int i = 0; i < 8; i++) a.prof[i] = pc[i];
+    if (a.prof && tid == 0) for (int i = 0; i < 24; i++) a.prof[i] = pc[i];
 }
