@@ -231,9 +231,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     iters_per_s = acc["lm_iterations"] / (dev_ms_max * 1e-3)
 
     # ---- end-to-end arm through bagpu_solve_ba with host buffers
-    res_buf = BAResult.alloc(p, s.max_trace)
+    res_buf = ctx.alloc_result(p, s)                         # page-locked, reused: what a SLAM thread's adapter keeps
     for _ in range(min(args.warmup, 2)):
-        ctx.solve_ba(p, s)
+        ctx.solve_ba(p, s, into=res_buf)
     barrier()
     e2e_s = 0.0
     e2e_passes = 0
@@ -242,7 +242,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         l2_flush()
         barrier()
         t0 = time.perf_counter()
-        ctx.solve_ba(p, s)
+        ctx.solve_ba(p, s, into=res_buf)
         e2e_s += time.perf_counter() - t0
         t = ctx.timing()
         e2e_passes += t["edge_linearisations"] + t["edge_evaluations"]

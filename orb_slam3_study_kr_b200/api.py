@@ -128,12 +128,22 @@ class Context:
                  p.obs_u, p.obs_v, p.obs_ur, p.obs_inv_sigma2)
 
     # -- BA
-    def solve_ba(self, problem: BAProblem, schedule: Schedule) -> BAResult:
+    def solve_ba(self, problem: BAProblem, schedule: Schedule, into=None) -> BAResult:
+        """One bagpu_solve_ba call with host buffers. `into` = a (result, CResult, trace) triple from alloc_result() to
+        reuse (and pin) the output buffers across calls, as a SLAM thread would."""
         cp, keep1 = problem.to_c()
         cs, keep2 = schedule.to_c()
-        res, cr, trace = BAResult.alloc(problem, schedule.max_trace)
+        res, cr, trace = into if into is not None else BAResult.alloc(problem, schedule.max_trace)
         self._check(self.lib.bagpu_solve_ba(self.h, C.byref(cp), C.byref(cs), C.byref(cr)))
         return res.finish(cr, trace)
+
+    def alloc_result(self, problem: BAProblem, schedule: Schedule, pinned: bool = True):
+        """Reusable output buffers for solve_ba / solve_resident (page-locked when `pinned`)."""
+        triple = BAResult.alloc(problem, schedule.max_trace)
+        if pinned:
+            r = triple[0]
+            self.pin(r.pose_qt, r.points, r.edge_chi2, r.edge_depth_pos, r.edge_level)
+        return triple
 
     def upload(self, problem: BAProblem):
         cp, keep = problem.to_c()

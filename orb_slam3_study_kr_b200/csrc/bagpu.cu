@@ -17,6 +17,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <chrono>
 
 #include "../../include/bagpu.h"
 #include "ba_kernels.cuh"
@@ -77,6 +80,24 @@ struct NcclApi {
 NcclApi g_nccl;
 
 enum { EV_BUILD = 0, EV_LINSOLVE = 1, EV_UPDATE = 2, EV_KINDS = 3 };
+
+}  // namespace
+
+namespace {
+// Host-side planning runs over millions of observations per upload: split the landmark / observation ranges over a few
+// threads (the calling SLAM thread blocks in bagpu_upload anyway). fn(thread, begin, end).
+template <class F>
+void parallel_ranges(int64_t n, int64_t min_chunk, F fn) {
+    static const int hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(hw, n / std::max<int64_t>(1, min_chunk)));
+    if (nt <= 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; t++) th.emplace_back([=] { fn(t, n * t / nt, n * (t + 1) / nt); });
+    fn(0, (int64_t)0, n / nt);
+    for (auto &x : th) x.join();
+}
+constexpr int kPlanThreads = 8;
 
 }  // namespace
 
@@ -325,15 +346,32 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     ctx->n_poses = Nt; ctx->n_points = Np; ctx->n_obs = Ne; ctx->n_cams = p->n_cameras; ctx->n_rigs = p->n_rigs;
     int64_t h2d = 0;
 
+    const bool dbg_t = getenv("BAGPU_DEBUG") != nullptr;
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tw0 = wall();
     // --- order: landmark-major, pose-ascending inside a landmark, insertion order preserved among equals
-    bool sorted = true;
-    for (int64_t e = 1; e < Ne; e++) {
-        const int a = p->obs_point[e - 1], b = p->obs_point[e];
-        if (a > b || (a == b && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted = false; break; }
-    }
+    std::atomic<bool> sorted_a{true};
+    parallel_ranges(Ne, 1 << 16, [&](int, int64_t e0, int64_t e1) {
+        for (int64_t e = std::max<int64_t>(1, e0); e < e1; e++) {
+            const int a = p->obs_point[e - 1], b = p->obs_point[e];
+            if (a > b || (a == b && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted_a.store(false, std::memory_order_relaxed); break; }
+        }
+    });
+    const bool sorted = sorted_a.load();
     std::vector<int> lm_ptr((size_t)Np + 1, 0);
-    for (int64_t e = 0; e < Ne; e++) lm_ptr[(size_t)p->obs_point[e] + 1]++;
-    for (int j = 0; j < Np; j++) lm_ptr[j + 1] += lm_ptr[j];
+    if (sorted) {
+        // boundaries of the runs: lm_ptr[j] = first observation of landmark j; landmarks without observations inherit the next one
+        std::fill(lm_ptr.begin(), lm_ptr.end(), -1);
+        parallel_ranges(Ne, 1 << 16, [&](int, int64_t e0, int64_t e1) {
+            for (int64_t e = e0; e < e1; e++)
+                if (e == 0 || p->obs_point[e - 1] != p->obs_point[e]) lm_ptr[(size_t)p->obs_point[e]] = (int)e;
+        });
+        lm_ptr[(size_t)Np] = (int)Ne;
+        for (int j = Np - 1; j >= 0; j--) if (lm_ptr[j] < 0) lm_ptr[j] = lm_ptr[j + 1];
+    } else {
+        for (int64_t e = 0; e < Ne; e++) lm_ptr[(size_t)p->obs_point[e] + 1]++;
+        for (int j = 0; j < Np; j++) lm_ptr[j + 1] += lm_ptr[j];
+    }
     std::vector<int> perm;
     if (!sorted) {
         perm.resize(Ne);
@@ -425,24 +463,33 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_pt_init.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_meta_init.p, ctx->d_o_meta.p, 4 * ne, cudaMemcpyDeviceToDevice, st));
 
+    const double tw1 = wall();
     // --- reduced camera system: envelope of Hschur from the landmark structure, band or dense storage
     const int n = 6 * nf;
     ctx->n_sys = n;
     {
         std::vector<int> lastrow(std::max(1, nf));
         for (int h = 0; h < nf; h++) lastrow[h] = h;
-        for (int j = 0; j < Np; j++) {
-            int mx = -1;
-            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                const int e = sorted ? a : perm[a];
-                mx = std::max(mx, ctx->h_hidx[p->obs_pose[e]]);
-            }
-            if (mx < 0) continue;
-            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                const int e = sorted ? a : perm[a];
-                const int h = ctx->h_hidx[p->obs_pose[e]];
-                if (h >= 0) lastrow[h] = std::max(lastrow[h], mx);
-            }
+        {
+            std::vector<std::vector<int>> part(kPlanThreads);
+            parallel_ranges(Np, 1 << 12, [&](int t, int64_t j0, int64_t j1) {
+                std::vector<int> &lr = part[t];
+                lr.assign(std::max(1, nf), -1);
+                for (int64_t j = j0; j < j1; j++) {
+                    int mx = -1;
+                    for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                        const int e = sorted ? a : perm[a];
+                        mx = std::max(mx, ctx->h_hidx[p->obs_pose[e]]);
+                    }
+                    if (mx < 0) continue;
+                    for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                        const int e = sorted ? a : perm[a];
+                        const int h = ctx->h_hidx[p->obs_pose[e]];
+                        if (h >= 0) lr[h] = std::max(lr[h], mx);
+                    }
+                }
+            });
+            for (auto &lr : part) for (size_t h = 0; h < lr.size() && (int)h < nf; h++) lastrow[h] = std::max(lastrow[h], lr[h]);
         }
         if (ctx->world > 1 && nf > 0) {
             // every rank must lay the reduced camera system out identically: the envelope is the union over the shards
@@ -475,6 +522,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));                       // col_end is a stack vector
     }
+    const double tw2 = wall();
     // --- plan of the tiled build (stage_kernel + apply_kernel): wide flags, record offsets, packed tasks, tiles, batches
     {
         std::vector<uint8_t> wide((size_t)Np, 0);
@@ -482,25 +530,33 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         std::vector<int> lo_of((size_t)Np, INT32_MAX), hi_of((size_t)Np, -1);
         int nw = 0;
         unsigned long long total = 0;
+        std::vector<uint8_t> ndist_of((size_t)Np, 0);
+        parallel_ranges(Np, 1 << 12, [&](int, int64_t j0, int64_t j1) {
+            for (int64_t j = j0; j < j1; j++) {
+                const int k = lm_ptr[j + 1] - lm_ptr[j];
+                int lo = INT32_MAX, hi = -1, run = 0, prevh = -2, ndist = 0;
+                bool w = k > 32;
+                for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
+                    const int h = ctx->h_hidx[p->obs_pose[sorted ? a : perm[a]]];
+                    if (h < 0) { prevh = -2; continue; }
+                    lo = std::min(lo, h); hi = std::max(hi, h);
+                    run = (h == prevh) ? run + 1 : 1;
+                    if (run == 1) ndist++;
+                    if (run > 2) w = true;                   // more than two edges on one (pose, point) pair
+                    prevh = h;
+                }
+                if (hi >= 0 && hi - lo + 1 > BT_MW) w = true;
+                if (ndist > BT_KT) w = true;                 // more distinct cameras than a record holds
+                lo_of[j] = lo; hi_of[j] = hi;
+                wide[j] = w ? 1 : 0;
+                ndist_of[j] = (uint8_t)std::min(ndist, 255);
+            }
+        });
         for (int j = 0; j < Np; j++) {
             const int k = lm_ptr[j + 1] - lm_ptr[j];
-            int lo = INT32_MAX, hi = -1, run = 0, prevh = -2, ndist = 0;
-            bool w = k > 32;
-            for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                const int h = ctx->h_hidx[p->obs_pose[sorted ? a : perm[a]]];
-                if (h < 0) { prevh = -2; continue; }
-                lo = std::min(lo, h); hi = std::max(hi, h);
-                run = (h == prevh) ? run + 1 : 1;
-                if (run == 1) ndist++;
-                if (run > 2) w = true;                       // more than two edges on one (pose, point) pair
-                prevh = h;
-            }
-            if (hi >= 0 && hi - lo + 1 > BT_MW) w = true;
-            if (ndist > BT_KT) w = true;                     // more distinct cameras than a record holds
-            lo_of[j] = lo; hi_of[j] = hi;
             rec_off[j] = (unsigned)total;
-            if (w) { wide[j] = 1; nw++; }
-            else if (k > 0) total += (unsigned long long)(BT_HDR + (ndist + 1) / 2 + 45 * ndist);
+            if (wide[j]) nw++;
+            else if (k > 0) total += (unsigned long long)(BT_HDR + (ndist_of[j] + 1) / 2 + 45 * ndist_of[j]);
         }
         rec_off[Np] = (unsigned)total;
         const bool tiled_ok = total < 0xffffffffull && n > 0;
@@ -590,11 +646,13 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(ctx->h_status.ensure(sizeof(double) * 32));
     ctx->pose_cur = ctx->d_pose_a.as<double>(); ctx->pose_trial = ctx->d_pose_b.as<double>();
     ctx->pt_cur = ctx->d_pt_a.as<double>(); ctx->pt_trial = ctx->d_pt_b.as<double>();
+    const double tw3 = wall();
     CK(cudaEventRecord(ctx->ev_phase[1], st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
     ctx->tm.h2d_ms = ms; ctx->tm.h2d_bytes = h2d;
+    if (dbg_t) fprintf(stderr, "[bagpu] upload host ms: order+copies %.2f envelope %.2f plan %.2f tail+sync %.2f | stream %.2f\n", tw1 - tw0, tw2 - tw1, tw3 - tw2, wall() - tw3, ms);
     ctx->have_problem = true;
     return BAGPU_OK;
 }
