@@ -13,8 +13,9 @@ A step = one Optimizer::GlobalBundleAdjustemnt call = optimize(20) from the init
           HBM, timed with CUDA events on the library's stream, max over ranks.
   e2e     the same metric through the reference-facing C-ABI call bagpu_solve_ba with HOST buffers: H2D of the whole
           problem, solve, D2H of poses / points / per-edge chi2 / flags inside the timed region.
-  roofline  the linearise+Schur kernel (build_kernel): algorithmic bytes per launch / mean launch duration (CUDA events
-          around every launch in the timed region) against the measured HBM copy bandwidth.
+  roofline  the linearise+Schur pass (stage_kernel + apply_kernel; build_kernel for the few wide landmarks), the dominant
+          kernel group: algorithmic bytes per pass / mean pass duration (CUDA events around every pass in the timed
+          region, on the library's stream) against the measured HBM copy bandwidth.
 """
 from __future__ import annotations
 
@@ -255,7 +256,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     build_avg_ms = acc["build_ms"] / max(1, acc["build_launches"])
     achieved = alg_bytes / (build_avg_ms * 1e-3) / 1e9
     traffic = None
-    tf = os.path.join(ROOT, "profiles", "build_kernel_traffic.json")
+    tf = os.path.join(ROOT, "profiles", "build_pass_traffic.json")
     if os.path.exists(tf):
         try:
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
@@ -276,7 +277,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(acc["total_launches"]),
                 "clocks": clk.summary(),
-                "roofline": {"kernel": "build_kernel (linearise + Hll + Schur scatter)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "linearise+Schur pass: stage_kernel + apply_kernel (+ build_kernel for wide landmarks)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": build_avg_ms,
                              "launches": int(acc["build_launches"])},

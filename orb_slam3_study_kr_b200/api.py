@@ -41,10 +41,11 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise BagpuError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    lib_path = os.environ.get("BAGPU_LIB", LIB_PATH)       # development override: an alternative build of the same ABI
+    if not os.path.exists(lib_path):
+        raise BagpuError(f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                          f"or `make -C {os.path.join(_HERE, 'csrc')}`. libbagpu has no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(lib_path)
     L.bagpu_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.bagpu_init.restype = C.c_int
     L.bagpu_destroy.argtypes = [C.c_void_p]

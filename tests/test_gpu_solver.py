@@ -1,0 +1,68 @@
+"""Reduced-camera-system solver (chol_band_kernel / chol_solve_kernel) against numpy, through the C ABI's unit-test hook
+bagpu_test_solve: (A + lambda I) x = b for symmetric positive definite A inside a monotone envelope col_end.
+Replaces LinearSolverEigen::solve (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _banded_spd(n, bw, rng, ragged=False):
+    ce = np.minimum(n - 1, np.arange(n) + bw)
+    if ragged:
+        ce = np.maximum.accumulate(np.minimum(n - 1, np.arange(n) + rng.integers(0, bw + 1, size=n)))
+    A = np.zeros((n, n))
+    for j in range(n):
+        v = rng.normal(size=ce[j] - j + 1)
+        A[j:ce[j] + 1, j] = v
+        A[j, j:ce[j] + 1] = v
+    A += np.eye(n) * (np.abs(A).sum(1).max() + 1.0)
+    return A, ce.astype(np.int32)
+
+
+# (n, half-bandwidth): one panel, partial last panel, dense, 2/4/8/16-CTA clusters, envelope beyond the band kernel (tiled kernel)
+SIZES = [(18, 17), (32, 10), (40, 39), (100, 30), (120, 119), (333, 60), (1000, 170), (900, 300), (700, 400)]
+
+
+@pytest.mark.parametrize("n,bw", SIZES)
+@pytest.mark.parametrize("ragged", [False, True])
+def test_solver_matches_numpy(ctx, n, bw, ragged):
+    rng = np.random.default_rng(n * 1000 + bw + int(ragged))
+    A, ce = _banded_spd(n, bw, rng, ragged)
+    b = rng.normal(size=n)
+    x, fail = ctx.test_solve(A, b, ce, 0.5)
+    ref = np.linalg.solve(A + 0.5 * np.eye(n), b)
+    assert not fail
+    assert np.abs(x - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n,h,env", [(300, 50, 90), (300, 50, 100), (300, 100, 100), (300, 50, 128), (600, 50, 100), (2994, 90, 180)])
+def test_solver_ill_conditioned(ctx, n, h, env):
+    """Badly scaled Gram matrices (metres next to radians: condition number ~1e8) whose true band is narrower than the
+    declared envelope; repeated to catch timing-dependent faults."""
+    rng = np.random.default_rng(1)
+    Bb = np.zeros((n, n + h))
+    for i in range(n):
+        Bb[i, i:i + h + 1] = rng.normal(size=h + 1)
+    A = Bb @ Bb.T
+    sc = 10.0 ** rng.uniform(-3, 3, size=n)
+    A = A * sc[:, None] * sc[None, :]
+    ce = np.minimum(n - 1, np.arange(n) + env).astype(np.int32)
+    b = rng.normal(size=n)
+    lam = 1e-8 * np.abs(np.diag(A)).max()
+    ref = np.linalg.solve(A + lam * np.eye(n), b)
+    for _ in range(3):
+        x, fail = ctx.test_solve(A, b, ce, lam)
+        assert not fail
+        assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_solver_flags_indefinite(ctx):
+    n = 200
+    A = np.eye(n)
+    A[50, 50] = -1.0
+    _, fail = ctx.test_solve(A, np.ones(n), np.minimum(n - 1, np.arange(n) + 20).astype(np.int32), 0.0)
+    assert fail
+    # and the context keeps working afterwards
+    x, fail = ctx.test_solve(np.eye(n) * 2.0, np.ones(n), np.minimum(n - 1, np.arange(n) + 20).astype(np.int32), 0.0)
+    assert not fail and np.allclose(x, 0.5)
