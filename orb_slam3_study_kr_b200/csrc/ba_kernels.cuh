@@ -79,7 +79,7 @@ struct BuildOut {
     double *hpp_diag;             // [6 n_free]  mode 0 only
     double *part_chi2;            // [gridDim.x]
     double *part_maxdiag;         // [gridDim.x] mode 0 only (Hll part)
-    const uint8_t *lm_wide;       // optional: build_kernel then handles only landmarks with lm_wide[j] != 0
+    const int *lm_list; int n_list;   // optional: build_kernel then handles only these landmarks (the "wide" ones)
 };
 
 __global__ void __launch_bounds__(BUILD_THREADS) build_kernel(BaDev D, const double *__restrict__ pose,
@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_kernel(BaDev D, const dou
     const int gw = blockIdx.x * BUILD_WARPS + warp, nw = gridDim.x * BUILD_WARPS;
     double chi_acc = 0.0, max_acc = 0.0;
 
-    for (int j = gw; j < D.n_points; j += nw) {
+    const int n_lm = O.lm_list ? O.n_list : D.n_points;
+    for (int jj = gw; jj < n_lm; jj += nw) {
+        const int j = O.lm_list ? __ldg(O.lm_list + jj) : jj;
         const int e0 = __ldg(D.lm_ptr + j), k = __ldg(D.lm_ptr + j + 1) - e0;
         if (k == 0) continue;
-        if (O.lm_wide && !O.lm_wide[j]) continue;
         const double X = __ldg(pt + 3 * (size_t)j), Y = __ldg(pt + 3 * (size_t)j + 1), Z = __ldg(pt + 3 * (size_t)j + 2);
         const int nchunk = (k + 31) >> 5;
         // ---- pass 1: Hll (6), bl (3), sum rho0
@@ -278,6 +279,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_kernel(BaDev D, const dou
 #define BT_KT 20                           // distinct free cameras per landmark a record can hold
 #define BT_HDR 10                          // record header doubles: n, Dinv(6), db(3)
 #define ST_THREADS 256
+#ifndef ST_MINB
+#define ST_MINB 2                          // resident CTAs per SM asked of the compiler for stage / update_packed
+#endif
 #define ST_WARPS (ST_THREADS / 32)
 #define AP_THREADS 1024
 #define AP_WARPS (AP_THREADS / 32)
@@ -300,7 +304,7 @@ struct StageArgs {
     double *part_chi2;            // [gridDim.x]
 };
 
-__global__ void __launch_bounds__(ST_THREADS) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
     __shared__ double s_chi[ST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0;
@@ -540,7 +544,7 @@ struct UpdateOut {
     double *edge_chi2;            // [n_obs] (sorted order)
     double *part_chi2;            // [gridDim.x]
     double *part_scale;           // [gridDim.x]  sum over landmarks of x_l (lambda x_l + b_l)
-    const uint8_t *lm_wide;       // optional: update_kernel then handles only landmarks with lm_wide[j] != 0
+    const int *lm_list; int n_list;   // optional: update_kernel then handles only these landmarks (the "wide" ones)
 };
 
 __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const double *__restrict__ pose,
@@ -549,9 +553,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const do
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * BUILD_WARPS + warp, nw = gridDim.x * BUILD_WARPS;
     double chi_acc = 0.0, sc_acc = 0.0;
-    for (int j = gw; j < D.n_points; j += nw) {
+    const int n_lm = O.lm_list ? O.n_list : D.n_points;
+    for (int jj = gw; jj < n_lm; jj += nw) {
+        const int j = O.lm_list ? __ldg(O.lm_list + jj) : jj;
         const int e0 = __ldg(D.lm_ptr + j), k = __ldg(D.lm_ptr + j + 1) - e0;
-        if (O.lm_wide && !O.lm_wide[j]) continue;
         const double X = __ldg(pt + 3 * (size_t)j), Y = __ldg(pt + 3 * (size_t)j + 1), Z = __ldg(pt + 3 * (size_t)j + 2);
         if (k == 0) {
             if (lane == 0) { O.pt_trial[3 * (size_t)j] = X; O.pt_trial[3 * (size_t)j + 1] = Y; O.pt_trial[3 * (size_t)j + 2] = Z; }
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const do
 // through update_kernel with a mask.
 struct UpdateTasks { const int2 *tasks; int n_tasks; };
 
-__global__ void __launch_bounds__(ST_THREADS) update_packed_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt,
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) update_packed_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt,
                                                                   UpdateOut O, UpdateTasks K) {
     __shared__ double s_chi[ST_WARPS], s_sc[ST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

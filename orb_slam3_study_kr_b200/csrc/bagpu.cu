@@ -117,7 +117,7 @@ struct bagpu_ctx {
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
-    DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_tasks, d_recoff, d_rec, d_batches;
+    DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_widelist, d_tasks, d_recoff, d_rec, d_batches;
     int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, upd_grid = 1, parts_stride = 1;
     size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
@@ -292,7 +292,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
-                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_tiles, &ctx->d_lmwide, &ctx->d_tasks, &ctx->d_recoff, &ctx->d_rec, &ctx->d_batches,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_tiles, &ctx->d_lmwide, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_recoff, &ctx->d_rec, &ctx->d_batches,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -609,6 +609,11 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         ctx->n_tiles = (int)tiles.size(); ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
         CK(ctx->d_lmwide.ensure((size_t)Np));
         CK(cudaMemcpyAsync(ctx->d_lmwide.p, wide.data(), (size_t)Np, cudaMemcpyHostToDevice, st));
+        std::vector<int> wide_list;
+        wide_list.reserve((size_t)nw);
+        for (int j = 0; j < Np; j++) if (wide[j]) wide_list.push_back(j);
+        CK(ctx->d_widelist.ensure(sizeof(int) * std::max<size_t>(1, wide_list.size())));
+        if (!wide_list.empty()) CK(cudaMemcpyAsync(ctx->d_widelist.p, wide_list.data(), sizeof(int) * wide_list.size(), cudaMemcpyHostToDevice, st));
         CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size())));
         if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
         {
@@ -785,7 +790,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             // computeLambdaInit: tau * max diagonal of Hpp and Hll (optimization_algorithm_levenberg.cpp:171-185)
             CK(cudaMemsetAsync(hpp, 0, sizeof(double) * std::max(1, n), st));
             BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
-            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_wide = nullptr;
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
             ctx->tm.total_launches++;
             int rc = all_reduce_sum(ctx, hpp, std::max(1, n)); if (rc) return rc;
@@ -805,7 +810,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (ctx->s_elems + 2 * (size_t)std::max(1, n)), st));
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
-            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_wide = nullptr;
+            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && ctx->n_tiles > 0 && !getenv("BAGPU_NO_TILES");
             bool have_wide_part = false;
             int n_part_b = G;
@@ -823,7 +828,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     apply_kernel<<<std::min(ctx->n_sm, ctx->n_tiles), AP_THREADS, sizeof(double) * AP_SMEM_DOUBLES, st>>>(AA);
                     ctx->tm.total_launches++;
                     if (ctx->n_wide > 0) {             // landmarks the window cannot hold: global-atomic path
-                        BuildOut OW = O; OW.part_chi2 = part_chi_w; OW.lm_wide = ctx->d_lmwide.as<uint8_t>();
+                        BuildOut OW = O; OW.part_chi2 = part_chi_w; OW.lm_list = ctx->d_widelist.as<int>(); OW.n_list = ctx->n_wide;
                         build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, OW);
                         have_wide_part = true; ctx->tm.total_launches++;
                     }
@@ -837,7 +842,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 cudaStreamSynchronize(st);
                 cudaMemcpy(a.data(), S, 8 * cnt, cudaMemcpyDeviceToHost);
                 cudaMemset(S, 0, 8 * cnt);
-                BuildOut OC = O; OC.lm_wide = nullptr; OC.part_chi2 = part_chi_w;
+                BuildOut OC = O; OC.lm_list = nullptr; OC.n_list = 0; OC.part_chi2 = part_chi_w;
                 build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, OC);
                 cudaStreamSynchronize(st);
                 cudaMemcpy(b2.data(), S, 8 * cnt, cudaMemcpyDeviceToHost);
@@ -860,7 +865,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
             UpdateOut U; U.lambda = lambda; U.xp = ctx->d_xp.as<double>(); U.pose_trial = ctx->pose_trial; U.pt_trial = ctx->pt_trial;
-            U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale; U.lm_wide = nullptr;
+            U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale; U.lm_list = nullptr; U.n_list = 0;
             const bool packed = ctx->n_tasks > 0 && !getenv("BAGPU_NO_TILES");
             int n_part_u = G; bool upd_wide = false;
             {
@@ -870,7 +875,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     update_packed_kernel<<<ctx->upd_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U, K);
                     n_part_u = ctx->upd_grid;
                     if (ctx->n_wide > 0) {
-                        UpdateOut UW = U; UW.part_chi2 = part_chi_uw; UW.part_scale = part_scale_w; UW.lm_wide = ctx->d_lmwide.as<uint8_t>();
+                        UpdateOut UW = U; UW.part_chi2 = part_chi_uw; UW.part_scale = part_scale_w; UW.lm_list = ctx->d_widelist.as<int>(); UW.n_list = ctx->n_wide;
                         update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, UW);
                         upd_wide = true; ctx->tm.total_launches++;
                     }
