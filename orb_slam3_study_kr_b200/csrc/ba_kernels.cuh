@@ -253,288 +253,13 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_kernel(BaDev D, const dou
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Tiled build (mode 1) = stage_kernel + apply_kernel. Same computation as build_kernel, but the Schur scatter of a TILE of
-// neighbouring landmarks is accumulated on chip and the two halves run at the occupancy each of them can reach.
-//
-// Landmarks arrive in creation order, so a run of them sees cameras from a narrow window [cbase, cbase + BT_MW) of
-// free-pose indices. The host cuts the landmark sequence into tiles for which this holds (landmarks wider than the
-// window, with more than BT_KT distinct free cameras, more than 32 observations or more than two edges on one pose are
-// "wide" and go through build_kernel's global-atomic path instead).
-//
-//   stage_kernel   lane = observation, several short tracks PACKED into one warp (a task = a run of whole landmarks with
-//                  <= 32 observations): linearise, segmented butterfly reduction of Hll / bl per landmark, invert, fold the
-//                  second edge of a (pose, point) pair into the first, and write one compact record per landmark to HBM:
-//                  [n | Dinv(6) | db(3) | hidx(n ints) | W(18 n) | w B^T B (21 n) | B^T g (6 n)].
-//   apply_kernel   one CTA of 32 warps per tile keeps the window's BT_MW(BT_MW+1)/2 upper 6x6 blocks in shared memory
-//                  (156 KB). Records stream through a staging buffer; warp w owns camera slot w, i.e. block row w of the
-//                  tile, so its read-modify-writes need neither atomics nor barriers. One pair block (a, b) is ONE
-//                  mma.sync.m8n8k4.f64: A = rows of W_a Dinv, B = rows of W_b (rank-3 product, k padded to 4).
-//                  One global RED per non-zero element per tile at the end.
-// Why (measured on B200, tests/micro/): scattered RED.F64 188 G/s, shared atomicAdd(double) 386 G/s (CAS loop), plain shared
-// RMW 1157 G/s; and a single fused kernel needs ~240 registers, i.e. 8 warps/SM, which leaves every phase latency-bound.
-#define BT_MW 32
-#define BT_NBLK (BT_MW * (BT_MW + 1) / 2)
-#define BT_BSTRIDE 37                      // 36 + 1 padding: spreads the blocks over the banks
-#define BT_KT 20                           // distinct free cameras per landmark a record can hold
-#define BT_HDR 10                          // record header doubles: n, Dinv(6), db(3)
+// Packed lanes (stage_kernel in schur_pairs.cuh, update_packed_kernel below): lane = observation, a task = a run of whole
+// landmarks with <= 32 observations in total, segmented butterfly reductions per landmark.
 #define ST_THREADS 256
 #ifndef ST_MINB
 #define ST_MINB 2                          // resident CTAs per SM asked of the compiler for stage / update_packed
 #endif
 #define ST_WARPS (ST_THREADS / 32)
-#define AP_THREADS 1024
-#define AP_WARPS (AP_THREADS / 32)
-#define AP_STG_DOUBLES 8192                // staging buffer of apply_kernel (64 KB)
-#define AP_MAX_LM 64                       // landmarks per batch
-#define AP_SMEM_DOUBLES (BT_NBLK * BT_BSTRIDE + 2 * BT_MW * 6 + AP_STG_DOUBLES)
-
-struct TileInfo { int begin, end, cbase, batch_begin, batch_end, pad; };
-struct BatchInfo { int lm_begin, lm_end; };
-
-BA_DEV int bt_block_index(int sa, int sb) { return sa * BT_MW - (sa * (sa - 1)) / 2 + (sb - sa); }   // sa <= sb
-BA_DEV int bt_rec_doubles(int n) { return BT_HDR + (n + 1) / 2 + 45 * n; }
-
-struct StageArgs {
-    const int2 *tasks;            // [n_tasks] landmark range [x, y) of a task: whole, non-wide landmarks, <= 32 observations
-    int n_tasks;
-    const unsigned *rec_off;      // [n_points + 1] record offsets in doubles
-    double *rec;                  // record pool
-    double lambda;
-    double *part_chi2;            // [gridDim.x]
-};
-
-__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
-    __shared__ double s_chi[ST_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double chi_acc = 0.0;
-    for (int t = blockIdx.x * ST_WARPS + warp; t < S.n_tasks; t += gridDim.x * ST_WARPS) {
-        const int2 tk = S.tasks[t];
-        const int e_first = __ldg(D.lm_ptr + tk.x), nobs = __ldg(D.lm_ptr + tk.y) - e_first;
-        const bool in = lane < nobs;
-        const int e = e_first + lane;
-        const int j = in ? __ldg(D.o_point + e) : -1;
-        int head = lane, segl = 1;
-        double X = 0, Y = 0, Z = 1;
-        if (in) {
-            const int p0 = __ldg(D.lm_ptr + j);
-            head = lane - (e - p0); segl = __ldg(D.lm_ptr + j + 1) - p0;
-            X = __ldg(pt + 3 * (size_t)j); Y = __ldg(pt + 3 * (size_t)j + 1); Z = __ldg(pt + 3 * (size_t)j + 2);
-        }
-        const int seg_last = head + segl - 1;
-        LaneEdge E;
-        lane_linearize(D, pose, X, Y, Z, e, in, E);
-        double r[10];
-        {
-            const double *A = E.L.A;
-            const double w = E.wgt;
-            r[0] = E.valid ? w * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6]) : 0.0;
-            r[1] = E.valid ? w * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7]) : 0.0;
-            r[2] = E.valid ? w * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8]) : 0.0;
-            r[3] = E.valid ? w * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7]) : 0.0;
-            r[4] = E.valid ? w * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8]) : 0.0;
-            r[5] = E.valid ? w * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8]) : 0.0;
-            r[6] = E.valid ? A[0] * E.g0 + A[3] * E.g1 + A[6] * E.g2 : 0.0;
-            r[7] = E.valid ? A[1] * E.g0 + A[4] * E.g1 + A[7] * E.g2 : 0.0;
-            r[8] = E.valid ? A[2] * E.g0 + A[5] * E.g1 + A[8] * E.g2 : 0.0;
-            r[9] = E.valid ? E.rho0 : 0.0;
-        }
-        // segmented reduction (fixed order): after the 5 steps the head lane of every landmark holds its sums
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const bool take = in && lane + off <= seg_last;
-#pragma unroll
-            for (int i = 0; i < 10; i++) {
-                const double o = __shfl_down_sync(0xffffffffu, r[i], off);
-                if (take) r[i] += o;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 10; i++) r[i] = __shfl_sync(0xffffffffu, r[i], head);
-        if (in && lane == head) chi_acc += r[9];
-        double di[6];
-        {
-            double h[6] = {r[0] + S.lambda, r[1], r[2], r[3] + S.lambda, r[4], r[5] + S.lambda};
-            if (!in) { h[0] = h[3] = h[5] = 1.0; h[1] = h[2] = h[4] = 0.0; }
-            sym3_inverse(h, di);
-        }
-        const bool hasp = E.valid && E.hidx >= 0;
-        const int ha = E.hidx;
-        // two edges on one (pose, point) pair sit in adjacent lanes of the same landmark: the second is folded into the first
-        const int hprev = __shfl_up_sync(0xffffffffu, ha, 1);
-        const bool vprev = __shfl_up_sync(0xffffffffu, (int)hasp, 1) != 0;
-        const bool follower = hasp && lane > head && vprev && hprev == ha;
-        const bool next_follows = (__shfl_down_sync(0xffffffffu, (int)follower, 1) != 0) && lane < 31;
-        const bool leader = hasp && !follower;
-        const unsigned lmask = __ballot_sync(0xffffffffu, leader);
-        const unsigned segmask = (segl >= 32 ? 0xffffffffu : ((1u << segl) - 1u)) << head;
-        const int q = __popc(lmask & segmask & ((1u << lane) - 1u));            // camera index inside the landmark
-        const int n = __popc(lmask & segmask);
-        double *rec = in ? S.rec + S.rec_off[j] : nullptr;
-        const double *A = E.L.A, *B = E.L.B;
-        const int hw = (n + 1) / 2;
-        if (in && lane == head) {
-            rec[0] = (double)n;
-#pragma unroll
-            for (int i = 0; i < 6; i++) rec[1 + i] = di[i];
-            rec[7] = di[0] * r[6] + di[1] * r[7] + di[2] * r[8];
-            rec[8] = di[1] * r[6] + di[3] * r[7] + di[4] * r[8];
-            rec[9] = di[2] * r[6] + di[4] * r[7] + di[5] * r[8];
-        }
-        if (leader) reinterpret_cast<int *>(rec + BT_HDR)[q] = ha;
-        // W (18), then w B^T B upper (21), then B^T g (6): own value + the follower's, written by the leader
-        {
-            double v[18];
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) v[3 * a + c] = hasp ? E.wgt * (B[a] * A[c] + B[6 + a] * A[3 + c] + B[12 + a] * A[6 + c]) : 0.0;
-#pragma unroll
-            for (int i = 0; i < 18; i++) { const double vn = __shfl_down_sync(0xffffffffu, v[i], 1); if (next_follows) v[i] += vn; }
-            if (leader) { double *dst = rec + BT_HDR + hw + 18 * q;
-#pragma unroll
-                for (int i = 0; i < 18; i++) dst[i] = v[i]; }
-        }
-        {
-            double v[21];
-            int p = 0;
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = a; c < 6; c++) { v[p] = hasp ? E.wgt * (B[a] * B[c] + B[6 + a] * B[6 + c] + B[12 + a] * B[12 + c]) : 0.0; p++; }
-#pragma unroll
-            for (int i = 0; i < 21; i++) { const double vn = __shfl_down_sync(0xffffffffu, v[i], 1); if (next_follows) v[i] += vn; }
-            if (leader) { double *dst = rec + BT_HDR + hw + 18 * n + 21 * q;
-#pragma unroll
-                for (int i = 0; i < 21; i++) dst[i] = v[i]; }
-        }
-        {
-            double v[6];
-#pragma unroll
-            for (int a = 0; a < 6; a++) v[a] = hasp ? (B[a] * E.g0 + B[6 + a] * E.g1 + B[12 + a] * E.g2) : 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) { const double vn = __shfl_down_sync(0xffffffffu, v[i], 1); if (next_follows) v[i] += vn; }
-            if (leader) { double *dst = rec + BT_HDR + hw + 39 * n + 6 * q;
-#pragma unroll
-                for (int i = 0; i < 6; i++) dst[i] = v[i]; }
-        }
-    }
-    chi_acc = warp_allsum(chi_acc);
-    if (lane == 0) s_chi[warp] = chi_acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double c = 0.0;
-        for (int w = 0; w < ST_WARPS; w++) c += s_chi[w];
-        S.part_chi2[blockIdx.x] = c;
-    }
-}
-
-struct ApplyArgs {
-    const TileInfo *tiles; int n_tiles;
-    const BatchInfo *batches;
-    const unsigned *rec_off;
-    const double *rec;
-    double *S; int ld; double *bp, *bs;
-};
-
-__global__ void __launch_bounds__(AP_THREADS) apply_kernel(ApplyArgs P) {
-    extern __shared__ double ap_sm[];
-    double *Sloc = ap_sm;                                  // [BT_NBLK][BT_BSTRIDE]
-    double *bploc = ap_sm + BT_NBLK * BT_BSTRIDE;          // [BT_MW][6]
-    double *bsloc = bploc + BT_MW * 6;                     // [BT_MW][6]
-    double *stg = bsloc + BT_MW * 6;                       // [AP_STG_DOUBLES]
-    __shared__ int s_loff[AP_MAX_LM + 1];
-    __shared__ unsigned char s_blk_sa[BT_NBLK];            // block index -> row slot (for the flush)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, q4 = lane & 3;
-    const bool lane_ok = g < 6 && q4 < 3;
-    const int c0 = 2 * q4;                                 // this lane's two output columns c0, c0+1
-    for (int sa = threadIdx.x; sa < BT_MW; sa += AP_THREADS)
-        for (int sb = sa; sb < BT_MW; sb++) s_blk_sa[bt_block_index(sa, sb)] = (unsigned char)sa;
-
-    for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const TileInfo T = P.tiles[t];
-        __syncthreads();
-        for (int i = threadIdx.x; i < BT_NBLK * BT_BSTRIDE + 2 * BT_MW * 6; i += AP_THREADS) ap_sm[i] = 0.0;
-        for (int b = T.batch_begin; b < T.batch_end; b++) {
-            const BatchInfo Bi = P.batches[b];
-            const int nl = Bi.lm_end - Bi.lm_begin;
-            const unsigned base = P.rec_off[Bi.lm_begin];
-            const int span = (int)(P.rec_off[Bi.lm_end] - base);
-            __syncthreads();                               // previous batch fully consumed (and the zeroing done)
-            for (int i = threadIdx.x; i < span; i += AP_THREADS) stg[i] = __ldg(P.rec + base + i);
-            for (int i = threadIdx.x; i <= nl; i += AP_THREADS) s_loff[i] = (int)(P.rec_off[Bi.lm_begin + i] - base);
-            __syncthreads();
-            // warp w owns camera slot w = block row w of the tile
-            for (int l = 0; l < nl; l++) {
-                if (s_loff[l + 1] == s_loff[l]) continue;                       // wide landmark: no record
-                const double *rc = stg + s_loff[l];
-                const int n = (int)rc[0];
-                if (n == 0) continue;
-                const int *hid = reinterpret_cast<const int *>(rc + BT_HDR);
-                const int myslot = (lane < n) ? hid[lane] - T.cbase : -1;
-                const unsigned hit = __ballot_sync(0xffffffffu, myslot == warp);
-                if (!hit) continue;
-                const int ia = __ffs(hit) - 1;
-                const int hw = (n + 1) / 2;
-                const double *W = rc + BT_HDR + hw, *H = W + 18 * n, *bv = H + 21 * n;
-                const int sa = warp;
-                // column q4 of Dinv (zero for the padded k = 3)
-                const double dq0 = (q4 == 0) ? rc[1] : (q4 == 1) ? rc[2] : (q4 == 2) ? rc[3] : 0.0;
-                const double dq1 = (q4 == 0) ? rc[2] : (q4 == 1) ? rc[4] : (q4 == 2) ? rc[5] : 0.0;
-                const double dq2 = (q4 == 0) ? rc[3] : (q4 == 1) ? rc[5] : (q4 == 2) ? rc[6] : 0.0;
-                double av = 0.0;
-                if (g < 6) { const double *w = W + ia * 18 + 3 * g; av = w[0] * dq0 + w[1] * dq1 + w[2] * dq2; }
-                double *rowbase = Sloc + (sa * BT_MW - (sa * (sa - 1)) / 2 - sa) * BT_BSTRIDE + 6 * g + c0;
-                {   // diagonal block: upper part, plus w B^T B
-                    const double bvv = lane_ok ? W[ia * 18 + 3 * g + q4] : 0.0;
-                    double m0, m1;
-                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-                        : "=d"(m0), "=d"(m1) : "d"(av), "d"(bvv), "d"(0.0), "d"(0.0));
-                    if (lane_ok) {
-                        const double *Hr = H + ia * 21 + (g * 6 - (g * (g - 1)) / 2) - g;   // Hr[c] = H(g,c), c >= g
-                        double *dst = rowbase + sa * BT_BSTRIDE;
-                        if (c0 >= g) dst[0] += Hr[c0] - m0;
-                        if (c0 + 1 >= g) dst[1] += Hr[c0 + 1] - m1;
-                    }
-                }
-#pragma unroll 4
-                for (int ib = ia + 1; ib < n; ib++) {
-                    const double bvv = lane_ok ? W[ib * 18 + 3 * g + q4] : 0.0;
-                    double m0, m1;
-                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-                        : "=d"(m0), "=d"(m1) : "d"(av), "d"(bvv), "d"(0.0), "d"(0.0));
-                    if (lane_ok) {
-                        double *dst = rowbase + (hid[ib] - T.cbase) * BT_BSTRIDE;
-                        dst[0] -= m0;
-                        dst[1] -= m1;
-                    }
-                }
-                if (lane < 6) {
-                    const double *w = W + ia * 18 + 3 * lane;
-                    bploc[6 * sa + lane] += bv[ia * 6 + lane];
-                    bsloc[6 * sa + lane] -= w[0] * rc[7] + w[1] * rc[8] + w[2] * rc[9];
-                }
-            }
-        }
-        __syncthreads();
-        // flush the tile: one global RED per non-zero element
-        for (int idx = threadIdx.x; idx < BT_NBLK * 36; idx += AP_THREADS) {
-            const int blk = idx / 36, e = idx - 36 * blk;
-            const double v = Sloc[blk * BT_BSTRIDE + e];
-            if (v == 0.0) continue;
-            const int sa = s_blk_sa[blk], sb = sa + (blk - bt_block_index(sa, sa));
-            const int r = e / 6, c = e - 6 * r;
-            atomicAdd(P.S + (size_t)(6 * (T.cbase + sa) + r) * P.ld + 6 * (T.cbase + sb) + c, v);
-        }
-        for (int idx = threadIdx.x; idx < BT_MW * 6; idx += AP_THREADS) {
-            const int h = T.cbase + idx / 6;
-            const double vb = bploc[idx], vs = bsloc[idx];
-            if (vb != 0.0) atomicAdd(P.bp + 6 * h + idx % 6, vb);
-            if (vs != 0.0) atomicAdd(P.bs + 6 * h + idx % 6, vs);
-        }
-    }
-}
 
 struct UpdateOut {
     double lambda;

@@ -22,7 +22,10 @@
 #include <chrono>
 
 #include "../../include/bagpu.h"
+#include <cub/cub.cuh>
+
 #include "ba_kernels.cuh"
+#include "schur_pairs.cuh"
 #include "chol.cuh"
 #include "pose_opt.cuh"
 
@@ -117,8 +120,10 @@ struct bagpu_ctx {
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
-    DevBuf d_y, d_colend, d_dinv, d_tiles, d_lmwide, d_widelist, d_tasks, d_recoff, d_rec, d_batches;
-    int n_tiles = 0, n_wide = 0, n_tasks = 0, stage_grid = 1, upd_grid = 1, parts_stride = 1;
+    DevBuf d_y, d_colend, d_dinv, d_widelist, d_tasks;
+    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp;
+    int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, parts_stride = 1;
+    int n_items = 0, pair_grid = 1; long long n_entries = 0;
     size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -292,7 +297,8 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
-                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_tiles, &ctx->d_lmwide, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_recoff, &ctx->d_rec, &ctx->d_batches,
+                      &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_Z, &ctx->d_Dr, &ctx->d_entries, &ctx->d_items, &ctx->d_pk_keys, &ctx->d_pk_keys2, &ctx->d_pk_vals,
+                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -523,118 +529,101 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         CK(cudaStreamSynchronize(st));                       // col_end is a stack vector
     }
     const double tw2 = wall();
-    // --- plan of the tiled build (stage_kernel + apply_kernel): wide flags, record offsets, packed tasks, tiles, batches
+    // --- plan of the linearise + Schur pass: packed tasks / wide list on the host (O(Np)), block-sorted pair lists on the device
     {
-        std::vector<uint8_t> wide((size_t)Np, 0);
-        std::vector<unsigned> rec_off((size_t)Np + 1, 0);
-        std::vector<int> lo_of((size_t)Np, INT32_MAX), hi_of((size_t)Np, -1);
-        int nw = 0;
-        unsigned long long total = 0;
-        std::vector<uint8_t> ndist_of((size_t)Np, 0);
-        parallel_ranges(Np, 1 << 12, [&](int, int64_t j0, int64_t j1) {
-            for (int64_t j = j0; j < j1; j++) {
-                const int k = lm_ptr[j + 1] - lm_ptr[j];
-                int lo = INT32_MAX, hi = -1, run = 0, prevh = -2, ndist = 0;
-                bool w = k > 32;
-                for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                    const int h = ctx->h_hidx[p->obs_pose[sorted ? a : perm[a]]];
-                    if (h < 0) { prevh = -2; continue; }
-                    lo = std::min(lo, h); hi = std::max(hi, h);
-                    run = (h == prevh) ? run + 1 : 1;
-                    if (run == 1) ndist++;
-                    if (run > 2) w = true;                   // more than two edges on one (pose, point) pair
-                    prevh = h;
-                }
-                if (hi >= 0 && hi - lo + 1 > BT_MW) w = true;
-                if (ndist > BT_KT) w = true;                 // more distinct cameras than a record holds
-                lo_of[j] = lo; hi_of[j] = hi;
-                wide[j] = w ? 1 : 0;
-                ndist_of[j] = (uint8_t)std::min(ndist, 255);
-            }
-        });
-        for (int j = 0; j < Np; j++) {
-            const int k = lm_ptr[j + 1] - lm_ptr[j];
-            rec_off[j] = (unsigned)total;
-            if (wide[j]) nw++;
-            else if (k > 0) total += (unsigned long long)(BT_HDR + (ndist_of[j] + 1) / 2 + 45 * ndist_of[j]);
-        }
-        rec_off[Np] = (unsigned)total;
-        const bool tiled_ok = total < 0xffffffffull && n > 0;
         std::vector<int2> tasks;
-        std::vector<TileInfo> tiles;
-        std::vector<BatchInfo> batches;
+        std::vector<int> wide_list;
         {
-            // tasks: runs of whole non-wide landmarks with <= 32 observations in total (stage_kernel, update_packed_kernel)
+            // tasks: runs of whole landmarks with <= 32 observations in total (stage_kernel, update_packed_kernel);
+            // a landmark with more than 32 observations is "wide" (stage_wide_kernel, update_kernel: warp = landmark)
             int tb = -1, tobs = 0;
             for (int j = 0; j <= Np; j++) {
                 const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
-                const bool brk = j == Np || wide[j];
+                const bool brk = j == Np || k > 32;
                 if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
                 if (!brk) { if (tb < 0) tb = j; tobs += k; }
+                else if (j < Np) wide_list.push_back(j);
             }
         }
-        if (tiled_ok) {
-            // tiles: runs of landmarks whose free cameras fit a window of BT_MW pose indices
-            const int tl_max = std::max(16, std::min(256, Np / (2 * ctx->n_sm)));
-            int begin = 0, cur_lo = INT32_MAX, cur_hi = -1, cur_cnt = 0;
-            auto close_tile = [&](int end) {
-                if (cur_cnt > 0) {
-                    TileInfo T; T.begin = begin; T.end = end; T.cbase = (cur_hi >= 0) ? cur_lo : 0; T.pad = 0;
-                    T.batch_begin = (int)batches.size();
-                    int bb = begin; unsigned bspan = 0;
-                    for (int j = begin; j <= end; j++) {
-                        const unsigned sz = (j < end) ? rec_off[j + 1] - rec_off[j] : 0;
-                        if (j == end || bspan + sz > AP_STG_DOUBLES || j - bb >= AP_MAX_LM) {
-                            if (j > bb) { BatchInfo B; B.lm_begin = bb; B.lm_end = j; batches.push_back(B); }
-                            bb = j; bspan = 0;
-                        }
-                        bspan += sz;
-                    }
-                    T.batch_end = (int)batches.size();
-                    tiles.push_back(T);
-                }
-                begin = end; cur_lo = INT32_MAX; cur_hi = -1; cur_cnt = 0;
-            };
-            for (int j = 0; j < Np; j++) {
-                if (wide[j]) { cur_cnt++; continue; }       // stays inside the tile's range; it has no record
-                if (hi_of[j] >= 0) {
-                    const int nlo = std::min(cur_lo, lo_of[j]), nhi = std::max(cur_hi, hi_of[j]);
-                    if (cur_cnt > 0 && (nhi - nlo + 1 > BT_MW || cur_cnt >= tl_max)) close_tile(j);
-                    cur_lo = std::min(cur_lo, lo_of[j]); cur_hi = std::max(cur_hi, hi_of[j]);
-                } else if (cur_cnt >= tl_max) close_tile(j);
-                cur_cnt++;
-            }
-            close_tile(Np);
-        }
-        ctx->n_tiles = (int)tiles.size(); ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
-        CK(ctx->d_lmwide.ensure((size_t)Np));
-        CK(cudaMemcpyAsync(ctx->d_lmwide.p, wide.data(), (size_t)Np, cudaMemcpyHostToDevice, st));
-        std::vector<int> wide_list;
-        wide_list.reserve((size_t)nw);
-        for (int j = 0; j < Np; j++) if (wide[j]) wide_list.push_back(j);
+        const int nw = (int)wide_list.size();
+        ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
         CK(ctx->d_widelist.ensure(sizeof(int) * std::max<size_t>(1, wide_list.size())));
         if (!wide_list.empty()) CK(cudaMemcpyAsync(ctx->d_widelist.p, wide_list.data(), sizeof(int) * wide_list.size(), cudaMemcpyHostToDevice, st));
         CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size())));
         if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
         {
-            int occ_u = 0;
+            int occ_u = 0, occ_st = 0, occ_sw = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, update_packed_kernel, ST_THREADS, 0));
             ctx->upd_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_u), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
-        }
-        if (ctx->n_tiles > 0) {
-            CK(ctx->d_tiles.ensure(sizeof(TileInfo) * tiles.size())); CK(ctx->d_batches.ensure(sizeof(BatchInfo) * std::max<size_t>(1, batches.size())));
-            CK(ctx->d_recoff.ensure(sizeof(unsigned) * ((size_t)Np + 1)));
-            CK(ctx->d_rec.ensure(sizeof(double) * std::max<unsigned long long>(1, total)));
-            CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, st));
-            if (!batches.empty()) CK(cudaMemcpyAsync(ctx->d_batches.p, batches.data(), sizeof(BatchInfo) * batches.size(), cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(ctx->d_recoff.p, rec_off.data(), sizeof(unsigned) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
-            int occ_st = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_st, stage_kernel, ST_THREADS, 0));
             ctx->stage_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_st), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sw, stage_wide_kernel, ST_THREADS, 0));
+            ctx->stage_wide_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_sw), (nw + ST_WARPS - 1) / ST_WARPS));
         }
-        CK(cudaStreamSynchronize(st));
-        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] tiled build: tiles=%d batches=%zu tasks=%d wide=%d records=%.1f MB stage_grid=%d\n",
-                                           ctx->n_tiles, batches.size(), ctx->n_tasks, nw, total * 8.0 / 1e6, ctx->stage_grid);
+        ctx->n_items = 0; ctx->n_entries = 0;
+        if (n > 0) {
+            // pair lists: for every upper block (a, b) of the reduced system the observation pairs (e_a, e_b) of the landmarks
+            // both cameras see, sorted by block (stable radix sort of the pairs generated in observation order).
+            const int bw1 = ctx->band_blocks + 1;
+            const long long nblk_ll = (long long)nf * bw1;
+            if (nblk_ll >= (1ll << 31)) return fail(ctx, BAGPU_ERR_ARG, "reduced system has too many blocks (%lld)", nblk_ll);
+            const int nblk = (int)nblk_ll;
+            CK(ctx->d_npairs.ensure(4 * (ne + 1))); CK(ctx->d_pairoff.ensure(4 * (ne + 1)));
+            CK(ctx->d_blkcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_blkoff.ensure(4 * ((size_t)nblk + 1)));
+            CK(ctx->d_itemcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_itemoff.ensure(4 * ((size_t)nblk + 1)));
+            unsigned *npairs = ctx->d_npairs.as<unsigned>(), *pairoff = ctx->d_pairoff.as<unsigned>();
+            unsigned *blkcnt = ctx->d_blkcnt.as<unsigned>(), *blkoff = ctx->d_blkoff.as<unsigned>();
+            unsigned *itemcnt = ctx->d_itemcnt.as<unsigned>(), *itemoff = ctx->d_itemoff.as<unsigned>();
+            CK(cudaMemsetAsync(blkcnt, 0, 4 * ((size_t)nblk + 1), st));
+            CK(cudaMemsetAsync(npairs + ne, 0, 4, st));
+            pair_count_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
+                                                 bw1, npairs, blkcnt);
+            pair_item_count_kernel<<<grid_for(nblk + 1, 256), 256, 0, st>>>(nblk + 1, blkcnt, itemcnt);
+            size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, npairs, pairoff, (int)(ne + 1), st));
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, blkcnt, blkoff, nblk + 1, st));
+            CK(ctx->d_cubtmp.ensure(std::max(tmp_a, tmp_b)));
+            size_t tmp = ctx->d_cubtmp.cap;
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, npairs, pairoff, (int)(ne + 1), st));
+            tmp = ctx->d_cubtmp.cap;
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, blkcnt, blkoff, nblk + 1, st));
+            tmp = ctx->d_cubtmp.cap;
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, itemcnt, itemoff, nblk + 1, st));
+            unsigned totals[2] = {0, 0};
+            CK(cudaMemcpyAsync(&totals[0], pairoff + ne, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&totals[1], itemoff + nblk, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const size_t npr = totals[0];
+            if (npr >= (1ull << 31)) return fail(ctx, BAGPU_ERR_ARG, "too many observation pairs for one device shard (%zu)", npr);
+            ctx->n_entries = (long long)npr; ctx->n_items = (int)totals[1];
+            if (npr > 0) {
+                CK(ctx->d_pk_keys.ensure(4 * npr)); CK(ctx->d_pk_keys2.ensure(4 * npr));
+                CK(ctx->d_pk_vals.ensure(8 * npr)); CK(ctx->d_entries.ensure(8 * npr));
+                CK(ctx->d_items.ensure(sizeof(PairItem) * (size_t)std::max(1, ctx->n_items)));
+                pair_gen_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
+                                                   bw1, pairoff, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_vals.as<int2>());
+                int end_bit = 1;
+                while (end_bit < 32 && (1ll << end_bit) < nblk_ll) end_bit++;
+                static_assert(sizeof(unsigned long long) == sizeof(int2), "pair entry size");
+                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_c, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
+                                                   ctx->d_pk_vals.as<unsigned long long>(), ctx->d_entries.as<unsigned long long>(), (int)npr, 0, end_bit, st));
+                CK(ctx->d_cubtmp.ensure(tmp_c));
+                tmp = ctx->d_cubtmp.cap;
+                CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, tmp, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
+                                                   ctx->d_pk_vals.as<unsigned long long>(), ctx->d_entries.as<unsigned long long>(), (int)npr, 0, end_bit, st));
+                pair_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, st>>>(nblk, bw1, blkoff, blkcnt, itemoff, ctx->d_items.as<PairItem>());
+                CK(cudaGetLastError());
+            }
+            CK(ctx->d_Z.ensure(sizeof(double) * ZR_STRIDE * ne)); CK(ctx->d_Dr.ensure(sizeof(double) * DR_STRIDE * ne));
+            static bool attr_set = false;
+            if (!attr_set) { CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES)); attr_set = true; }
+            int occ_p = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, PK_THREADS, PK_SMEM_BYTES));
+            ctx->pair_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_p), (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
+        }
+        CK(cudaStreamSynchronize(st));                       // tasks / wide_list are stack vectors
+        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
+                                           ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
     CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n))));
     CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
@@ -643,7 +632,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
-    ctx->parts_stride = std::max(std::max(ctx->build_grid, ctx->stage_grid), ctx->upd_grid);
+    ctx->parts_stride = std::max(std::max(std::max(ctx->build_grid, ctx->stage_grid), ctx->stage_wide_grid), ctx->upd_grid);
     CK(ctx->d_parts.ensure(sizeof(double) * 7 * (size_t)ctx->parts_stride));
     CK(ctx->d_status.ensure(sizeof(double) * 32));
     CK(ctx->d_fail.ensure(sizeof(int) * 4));
@@ -811,26 +800,26 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
-            const bool tiled = n > 0 && ctx->n_tiles > 0 && !getenv("BAGPU_NO_TILES");
+            const bool tiled = n > 0 && !getenv("BAGPU_NO_TILES");
             bool have_wide_part = false;
-            int n_part_b = G;
+            int n_part_b = G, n_part_w = G;
             {
                 ScopedEv ev(ctx, EV_BUILD);
                 if (tiled) {
-                    static bool attr_set = false;
-                    if (!attr_set) { CK(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * AP_SMEM_DOUBLES))); attr_set = true; }
-                    StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.rec_off = ctx->d_recoff.as<unsigned>();
-                    SA.rec = ctx->d_rec.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b;
+                    StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
+                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.fail = ctx->d_fail.as<int>();
                     stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                     n_part_b = ctx->stage_grid;
-                    ApplyArgs AA; AA.tiles = ctx->d_tiles.as<TileInfo>(); AA.n_tiles = ctx->n_tiles; AA.batches = ctx->d_batches.as<BatchInfo>();
-                    AA.rec_off = ctx->d_recoff.as<unsigned>(); AA.rec = ctx->d_rec.as<double>(); AA.S = S; AA.ld = ld; AA.bp = bp; AA.bs = bs;
-                    apply_kernel<<<std::min(ctx->n_sm, ctx->n_tiles), AP_THREADS, sizeof(double) * AP_SMEM_DOUBLES, st>>>(AA);
-                    ctx->tm.total_launches++;
-                    if (ctx->n_wide > 0) {             // landmarks the window cannot hold: global-atomic path
-                        BuildOut OW = O; OW.part_chi2 = part_chi_w; OW.lm_list = ctx->d_widelist.as<int>(); OW.n_list = ctx->n_wide;
-                        build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, OW);
-                        have_wide_part = true; ctx->tm.total_launches++;
+                    if (ctx->n_wide > 0) {             // landmarks with more than 32 observations: warp = landmark
+                        StageArgs SW = SA; SW.part_chi2 = part_chi_w;
+                        stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
+                        have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
+                    }
+                    if (ctx->n_items > 0) {
+                        PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
+                        PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
+                        pair_kernel<<<ctx->pair_grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+                        ctx->tm.total_launches++;
                     }
                 } else {
                     build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O);
@@ -886,7 +875,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             ctx->tm.total_launches += 2;
             ctx->tm.edge_linearisations += 0; ctx->tm.edge_evaluations += n_active;
             // dstat[0] = chi2 at the linearisation point, [1] = trial chi2, [2] = landmark part of scale, [4] = pose part of scale
-            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_b, part_chi_b, nullptr, nullptr, nullptr, nullptr, 0, dstat + 12, have_wide_part ? part_chi_w : nullptr, G);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_b, part_chi_b, nullptr, nullptr, nullptr, nullptr, 0, dstat + 12, have_wide_part ? part_chi_w : nullptr, n_part_w);
             reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_chi_u, nullptr, nullptr, nullptr, nullptr, 0, dstat + 16, upd_wide ? part_chi_uw : nullptr, G);
             reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8, upd_wide ? part_scale_w : nullptr, G);
             ctx->tm.total_launches += 3;

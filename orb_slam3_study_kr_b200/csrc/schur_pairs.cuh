@@ -1,0 +1,363 @@
+// Linearise + Schur pass, pair-major (sm_100a).
+//
+// Replaces BlockSolver::buildSystem + setLambda + the landmark loop of BlockSolver::solve
+// (Thirdparty/g2o/g2o/core/block_solver.hpp:501-560, 373-444) by two kernels that never read-modify-write the reduced
+// camera system while they accumulate:
+//
+//   stage_kernel / stage_wide_kernel   landmark-major (lane = observation). Linearise, reduce the landmark's Hll / bl,
+//       factor Hll + lambda I = L L^T (3x3 Cholesky, in registers) and write per observation
+//         Z  = W L^-T                      (6x3; W = rho1 w B^T A is the Hpl block)   -> Z Z'^T = W (Hll+lambda I)^-1 W'^T
+//         Dr = [ w B^T B (21) | B^T g (6) | -Z L^-1 bl (6) ]                          -> the per-camera sums
+//   pair_kernel    camera-pair-major. At upload the device lists, for every upper block (a, b) of the reduced system,
+//       the observation pairs (e_a, e_b) of the landmarks both cameras see, sorted by block (pair_plan_*). A warp takes
+//       one chunk of one block's list, each lane accumulates Z_a Z_b^T of its entries in 36 registers, the warp sums the
+//       lanes once and issues 36 REDs per chunk. The block is a contraction over its shared landmarks, so the work per
+//       entry is two 144-byte gathers (L2 resident: neighbouring blocks share the records) and 108 DFMA.
+//       Diagonal blocks also sum the Dr records of their camera (Hpp, bp, bs).
+//
+// Any track length, any number of edges on one (pose, point) pair and any camera span go through the same path.
+#pragma once
+#include "ba_kernels.cuh"
+
+#define ZR_STRIDE 18
+#define DR_STRIDE 34
+#define PK_CHUNK 512                       // entries per work item
+#define PK_THREADS 128
+#define PK_WARPS (PK_THREADS / 32)
+#define PK_RED_LD 33
+#define PK_SMEM_BYTES (PK_WARPS * 36 * PK_RED_LD * 8)
+
+struct PairItem { int a, b, begin, end; };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plan (upload): observations are sorted landmark-major / pose-ascending, free-pose indices are monotone in the pose index,
+// so inside a landmark e <= e2 implies hidx(e) <= hidx(e2): every pair lands in the upper triangle.
+// Block id = a * bw1 + (b - a) with bw1 = band_blocks + 1 (the envelope agreed at upload bounds b - a).
+__global__ void pair_count_kernel(int64_t n_obs, const int *__restrict__ lm_ptr, const int *__restrict__ o_pose,
+                                  const int *__restrict__ o_point, const int *__restrict__ hidx, int bw1,
+                                  unsigned *__restrict__ npairs, unsigned *blk_cnt) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_obs) return;
+    const int ha = hidx[o_pose[e]];
+    unsigned cnt = 0;
+    if (ha >= 0) {
+        const int end = lm_ptr[o_point[e] + 1];
+        for (int e2 = (int)e; e2 < end; e2++) {
+            const int hb = hidx[o_pose[e2]];
+            if (hb < 0) continue;
+            cnt++;
+            atomicAdd(blk_cnt + (size_t)ha * bw1 + (hb - ha), 1u);
+        }
+    }
+    npairs[e] = cnt;
+}
+
+__global__ void pair_gen_kernel(int64_t n_obs, const int *__restrict__ lm_ptr, const int *__restrict__ o_pose,
+                                const int *__restrict__ o_point, const int *__restrict__ hidx, int bw1,
+                                const unsigned *__restrict__ pair_off, unsigned *__restrict__ keys, int2 *__restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_obs) return;
+    const int ha = hidx[o_pose[e]];
+    if (ha < 0) return;
+    const int end = lm_ptr[o_point[e] + 1];
+    unsigned pos = pair_off[e];
+    for (int e2 = (int)e; e2 < end; e2++) {
+        const int hb = hidx[o_pose[e2]];
+        if (hb < 0) continue;
+        keys[pos] = (unsigned)ha * (unsigned)bw1 + (unsigned)(hb - ha);
+        vals[pos] = make_int2((int)e, e2);
+        pos++;
+    }
+}
+
+__global__ void pair_item_count_kernel(int nblk, const unsigned *__restrict__ blk_cnt, unsigned *__restrict__ item_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nblk) item_cnt[i] = (blk_cnt[i] + PK_CHUNK - 1) / PK_CHUNK;
+}
+
+__global__ void pair_item_fill_kernel(int nblk, int bw1, const unsigned *__restrict__ blk_off, const unsigned *__restrict__ blk_cnt,
+                                      const unsigned *__restrict__ item_off, PairItem *__restrict__ items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk) return;
+    const unsigned cnt = blk_cnt[i];
+    if (!cnt) return;
+    const int a = i / bw1, b = a + (i - a * bw1);
+    const unsigned off = blk_off[i];
+    unsigned io = item_off[i];
+    for (unsigned c = 0; c < cnt; c += PK_CHUNK) {
+        PairItem I; I.a = a; I.b = b; I.begin = (int)(off + c); I.end = (int)(off + min(cnt, c + PK_CHUNK));
+        items[io++] = I;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage
+struct LmFactor { double i00, l10, l20, i11, l21, i22, c0, c1, c2; };
+
+// r = [Hll 00 01 02 11 12 22 | bl 0 1 2]; Hll + lambda I = L L^T, c = L^-1 bl. false if a pivot is not positive.
+BA_DEV bool lm_factor(const double *r, double lambda, LmFactor &F) {
+    const double h0 = r[0] + lambda, h3 = r[3] + lambda, h5 = r[5] + lambda;
+    bool ok = h0 > 0.0;
+    F.i00 = 1.0 / sqrt(h0);
+    F.l10 = r[1] * F.i00; F.l20 = r[2] * F.i00;
+    const double p1 = h3 - F.l10 * F.l10;
+    ok = ok && p1 > 0.0;
+    F.i11 = 1.0 / sqrt(p1);
+    F.l21 = (r[4] - F.l20 * F.l10) * F.i11;
+    const double p2 = h5 - F.l20 * F.l20 - F.l21 * F.l21;
+    ok = ok && p2 > 0.0;
+    F.i22 = 1.0 / sqrt(p2);
+    if (!ok) { F.i00 = F.i11 = F.i22 = 0.0; F.l10 = F.l20 = F.l21 = 0.0; }
+    F.c0 = r[6] * F.i00;
+    F.c1 = (r[7] - F.l10 * F.c0) * F.i11;
+    F.c2 = (r[8] - F.l20 * F.c0 - F.l21 * F.c1) * F.i22;
+    return ok;
+}
+
+// the landmark's contribution to Hll (6), bl (3) and the robustified cost (1) of one lane
+BA_DEV void lane_hll(const LaneEdge &E, double *r) {
+    const double *A = E.L.A;
+    const double w = E.wgt;
+    r[0] = E.valid ? w * (A[0] * A[0] + A[3] * A[3] + A[6] * A[6]) : 0.0;
+    r[1] = E.valid ? w * (A[0] * A[1] + A[3] * A[4] + A[6] * A[7]) : 0.0;
+    r[2] = E.valid ? w * (A[0] * A[2] + A[3] * A[5] + A[6] * A[8]) : 0.0;
+    r[3] = E.valid ? w * (A[1] * A[1] + A[4] * A[4] + A[7] * A[7]) : 0.0;
+    r[4] = E.valid ? w * (A[1] * A[2] + A[4] * A[5] + A[7] * A[8]) : 0.0;
+    r[5] = E.valid ? w * (A[2] * A[2] + A[5] * A[5] + A[8] * A[8]) : 0.0;
+    r[6] = E.valid ? A[0] * E.g0 + A[3] * E.g1 + A[6] * E.g2 : 0.0;
+    r[7] = E.valid ? A[1] * E.g0 + A[4] * E.g1 + A[7] * E.g2 : 0.0;
+    r[8] = E.valid ? A[2] * E.g0 + A[5] * E.g1 + A[8] * E.g2 : 0.0;
+    r[9] = E.valid ? E.rho0 : 0.0;
+}
+
+// write the Z and Dr records of observation e (free pose). Inactive (level-1) edges write exact zeros.
+BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *__restrict__ Zp, double *__restrict__ Dp) {
+    const bool act = E.valid;
+    const double *A = E.L.A, *B = E.L.B;
+    double2 *zo = reinterpret_cast<double2 *>(Zp + ZR_STRIDE * e);
+    double2 *dout = reinterpret_cast<double2 *>(Dp + DR_STRIDE * e);
+    double z[18], bs[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        const double w0 = act ? E.wgt * (B[a] * A[0] + B[6 + a] * A[3] + B[12 + a] * A[6]) : 0.0;
+        const double w1 = act ? E.wgt * (B[a] * A[1] + B[6 + a] * A[4] + B[12 + a] * A[7]) : 0.0;
+        const double w2 = act ? E.wgt * (B[a] * A[2] + B[6 + a] * A[5] + B[12 + a] * A[8]) : 0.0;
+        const double z0 = w0 * F.i00;
+        const double z1 = (w1 - z0 * F.l10) * F.i11;
+        const double z2 = (w2 - z0 * F.l20 - z1 * F.l21) * F.i22;
+        z[3 * a] = z0; z[3 * a + 1] = z1; z[3 * a + 2] = z2;
+        bs[a] = -(z0 * F.c0 + z1 * F.c1 + z2 * F.c2);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) zo[i] = make_double2(z[2 * i], z[2 * i + 1]);
+    double d[DR_STRIDE];
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int c = a; c < 6; c++) { d[p] = act ? E.wgt * (B[a] * B[c] + B[6 + a] * B[6 + c] + B[12 + a] * B[12 + c]) : 0.0; p++; }
+#pragma unroll
+    for (int a = 0; a < 6; a++) d[21 + a] = act ? (B[a] * E.g0 + B[6 + a] * E.g1 + B[12 + a] * E.g2) : 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) d[27 + a] = bs[a];
+    d[33] = 0.0;
+#pragma unroll
+    for (int i = 0; i < DR_STRIDE / 2; i++) dout[i] = make_double2(d[2 * i], d[2 * i + 1]);
+}
+
+struct StageArgs {
+    const int2 *tasks;            // [n_tasks] landmark range [x, y): whole landmarks, <= 32 observations in total
+    int n_tasks;
+    const int *lm_list; int n_list;   // stage_wide_kernel: landmarks with more than 32 observations
+    double *Z, *Dr;
+    double lambda;
+    double *part_chi2;            // [gridDim.x]
+    int *fail;
+};
+
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
+    __shared__ double s_chi[ST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double chi_acc = 0.0;
+    bool bad = false;
+    for (int t = blockIdx.x * ST_WARPS + warp; t < S.n_tasks; t += gridDim.x * ST_WARPS) {
+        const int2 tk = S.tasks[t];
+        const int e_first = __ldg(D.lm_ptr + tk.x), nobs = __ldg(D.lm_ptr + tk.y) - e_first;
+        const bool in = lane < nobs;
+        const int e = e_first + lane;
+        const int j = in ? __ldg(D.o_point + e) : -1;
+        int head = lane, segl = 1;
+        double X = 0, Y = 0, Z = 1;
+        if (in) {
+            const int p0 = __ldg(D.lm_ptr + j);
+            head = lane - (e - p0); segl = __ldg(D.lm_ptr + j + 1) - p0;
+            X = __ldg(pt + 3 * (size_t)j); Y = __ldg(pt + 3 * (size_t)j + 1); Z = __ldg(pt + 3 * (size_t)j + 2);
+        }
+        const int seg_last = head + segl - 1;
+        LaneEdge E;
+        lane_linearize(D, pose, X, Y, Z, e, in, E);
+        double r[10];
+        lane_hll(E, r);
+        // segmented reduction (fixed order): after the 5 steps the head lane of every landmark holds its sums
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const bool take = in && lane + off <= seg_last;
+#pragma unroll
+            for (int i = 0; i < 10; i++) {
+                const double o = __shfl_down_sync(0xffffffffu, r[i], off);
+                if (take) r[i] += o;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) r[i] = __shfl_sync(0xffffffffu, r[i], head);
+        if (in && lane == head) chi_acc += r[9];
+        LmFactor F;
+        const bool ok = lm_factor(r, S.lambda, F);
+        if (in && !ok) bad = true;
+        // level-1 edges on a free pose still own a record (the pair lists do not change between rounds): exact zeros
+        const int hx = in ? __ldg(D.pose_hidx + __ldg(D.o_pose + e)) : -1;
+        if (hx >= 0) lane_emit(E, F, e, S.Z, S.Dr);
+    }
+    if (bad) atomicOr(S.fail, 1);
+    chi_acc = warp_allsum(chi_acc);
+    if (lane == 0) s_chi[warp] = chi_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) c += s_chi[w];
+        S.part_chi2[blockIdx.x] = c;
+    }
+}
+
+// the same for landmarks with more than 32 observations: warp = landmark, two passes over its chunks
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
+    __shared__ double s_chi[ST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double chi_acc = 0.0;
+    bool bad = false;
+    for (int jj = blockIdx.x * ST_WARPS + warp; jj < S.n_list; jj += gridDim.x * ST_WARPS) {
+        const int j = __ldg(S.lm_list + jj);
+        const int e0 = __ldg(D.lm_ptr + j), k = __ldg(D.lm_ptr + j + 1) - e0;
+        if (k == 0) continue;
+        const double X = __ldg(pt + 3 * (size_t)j), Y = __ldg(pt + 3 * (size_t)j + 1), Z = __ldg(pt + 3 * (size_t)j + 2);
+        const int nchunk = (k + 31) >> 5;
+        double acc[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) acc[i] = 0.0;
+        LaneEdge E;
+        for (int c = 0; c < nchunk; c++) {
+            lane_linearize(D, pose, X, Y, Z, e0 + 32 * c + lane, 32 * c + lane < k, E);
+            double r[10];
+            lane_hll(E, r);
+#pragma unroll
+            for (int i = 0; i < 10; i++) acc[i] += r[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) acc[i] = warp_allsum(acc[i]);
+        chi_acc += acc[9];
+        LmFactor F;
+        if (!lm_factor(acc, S.lambda, F)) bad = true;
+        for (int c = 0; c < nchunk; c++) {
+            const bool in = 32 * c + lane < k;
+            lane_linearize(D, pose, X, Y, Z, e0 + 32 * c + lane, in, E);
+            const int hx = in ? __ldg(D.pose_hidx + __ldg(D.o_pose + e0 + 32 * c + lane)) : -1;
+            if (hx >= 0) lane_emit(E, F, e0 + 32 * c + lane, S.Z, S.Dr);
+        }
+    }
+    if (bad) atomicOr(S.fail, 1);
+    if (lane == 0) s_chi[warp] = chi_acc;          // warp_allsum left the same value in every lane
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) c += s_chi[w];
+        S.part_chi2[blockIdx.x] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pair
+struct PairArgs {
+    const PairItem *items; int n_items;
+    const int2 *entries;
+    const double *Z, *Dr;
+    double *S; int ld; double *bp, *bs;
+};
+
+// acc (6x6, row-major) += Z_x Z_y^T
+BA_DEV void pair_accumulate(const double *__restrict__ Z, int ex, int ey, double *acc) {
+    const double2 *px = reinterpret_cast<const double2 *>(Z + ZR_STRIDE * (size_t)ex);
+    const double2 *py = reinterpret_cast<const double2 *>(Z + ZR_STRIDE * (size_t)ey);
+    double x[18], y[18];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double2 v = __ldg(py + i); y[2 * i] = v.x; y[2 * i + 1] = v.y; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double2 v = __ldg(px + i); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            acc[6 * r + c] += x[3 * r] * y[3 * c] + x[3 * r + 1] * y[3 * c + 1] + x[3 * r + 2] * y[3 * c + 2];
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
+    extern __shared__ double pk_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *red = pk_sm + warp * 36 * PK_RED_LD;
+    for (int it = blockIdx.x * PK_WARPS + warp; it < P.n_items; it += gridDim.x * PK_WARPS) {
+        const PairItem I = P.items[it];
+        const bool diag = I.a == I.b;
+        double *Sblk = P.S + (size_t)(6 * I.a) * P.ld + 6 * I.b;
+        {
+            double acc[36];
+#pragma unroll
+            for (int i = 0; i < 36; i++) acc[i] = 0.0;
+            for (int i = I.begin + lane; i < I.end; i += 32) {
+                const int2 en = __ldg(P.entries + i);
+                pair_accumulate(P.Z, en.x, en.y, acc);
+                if (diag && en.x != en.y) pair_accumulate(P.Z, en.y, en.x, acc);     // two edges on one (pose, point): M + M^T
+            }
+#pragma unroll
+            for (int i = 0; i < 36; i++) red[i * PK_RED_LD + lane] = acc[i];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int o = lane; o < 36; o += 32) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) s += red[o * PK_RED_LD + l];
+            const int r = o / 6, c = o - 6 * r;
+            if ((!diag || c >= r) && s != 0.0) atomicAdd(Sblk + (size_t)r * P.ld + c, -s);
+        }
+        __syncwarp();
+        if (diag) {
+            // Hpp, bp, bs of camera a: sum of the Dr records of its observations (the (e, e) entries)
+            double d[DR_STRIDE];
+#pragma unroll
+            for (int i = 0; i < DR_STRIDE; i++) d[i] = 0.0;
+            for (int i = I.begin + lane; i < I.end; i += 32) {
+                const int2 en = __ldg(P.entries + i);
+                if (en.x != en.y) continue;
+                const double2 *pd = reinterpret_cast<const double2 *>(P.Dr + DR_STRIDE * (size_t)en.x);
+#pragma unroll
+                for (int q = 0; q < DR_STRIDE / 2; q++) { const double2 v = __ldg(pd + q); d[2 * q] += v.x; d[2 * q + 1] += v.y; }
+            }
+#pragma unroll
+            for (int i = 0; i < DR_STRIDE - 1; i++) red[i * PK_RED_LD + lane] = d[i];
+            __syncwarp();
+#pragma unroll 1
+            for (int o = lane; o < DR_STRIDE - 1; o += 32) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; l++) s += red[o * PK_RED_LD + l];
+                if (s == 0.0) continue;
+                if (o < 21) {
+                    int r = 0, t = o;
+                    while (t >= 6 - r) { t -= 6 - r; r++; }
+                    atomicAdd(Sblk + (size_t)r * P.ld + r + t, s);
+                } else if (o < 27) atomicAdd(P.bp + 6 * I.a + (o - 21), s);
+                else atomicAdd(P.bs + 6 * I.a + (o - 27), s);
+            }
+            __syncwarp();
+        }
+    }
+}
