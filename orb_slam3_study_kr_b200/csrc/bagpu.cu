@@ -108,6 +108,8 @@ struct bagpu_ctx {
     int device = 0;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_chol = nullptr;    // the band Cholesky runs beside pair_kernel on its own (high-priority) stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     char err[512] = {0};
     // ---- communicator (multi-GPU global BA)
     ncclComm_t comm = nullptr; int world = 1, rank = 0;
@@ -121,9 +123,9 @@ struct bagpu_ctx {
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_widelist, d_tasks;
-    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp;
+    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone;
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, parts_stride = 1;
-    int n_items = 0, pair_grid = 1; long long n_entries = 0;
+    int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
     size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -180,9 +182,9 @@ cudaEvent_t get_event(bagpu_ctx *ctx) {
     return ctx->ev_pool[ctx->ev_used++];
 }
 struct ScopedEv {
-    bagpu_ctx *c; cudaEvent_t a, b; int kind;
-    ScopedEv(bagpu_ctx *ctx, int k) : c(ctx), kind(k) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
-    ~ScopedEv() { cudaEventRecord(b, c->stream); c->pending.push_back({a, b, kind}); }
+    bagpu_ctx *c; cudaEvent_t a, b; int kind; cudaStream_t s;
+    ScopedEv(bagpu_ctx *ctx, int k, cudaStream_t stream = nullptr) : c(ctx), kind(k), s(stream ? stream : ctx->stream) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, s); }
+    ~ScopedEv() { cudaEventRecord(b, s); c->pending.push_back({a, b, kind}); }
 };
 void resolve_events(bagpu_ctx *ctx) {      // call after a stream sync
     for (auto &p : ctx->pending) {
@@ -284,6 +286,12 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAGPU_ERR_CUDA; }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->stream_chol, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return BAGPU_ERR_CUDA; }
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev_phase[i]);
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     *out = ctx;
@@ -298,7 +306,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
                       &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_Z, &ctx->d_Dr, &ctx->d_entries, &ctx->d_items, &ctx->d_pk_keys, &ctx->d_pk_keys2, &ctx->d_pk_vals,
-                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp,
+                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp, &ctx->d_rowdone,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -306,6 +314,10 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     ctx->h_status.release(); ctx->h_stage.release();
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; i++) if (ctx->ev_phase[i]) cudaEventDestroy(ctx->ev_phase[i]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    cudaStreamSynchronize(ctx->stream_chol);
+    cudaStreamDestroy(ctx->stream_chol);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -556,7 +568,8 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, update_packed_kernel, ST_THREADS, 0));
             ctx->upd_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_u), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_st, stage_kernel, ST_THREADS, 0));
-            ctx->stage_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_st), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
+            ctx->stage_occ = std::max(1, occ_st);
+            ctx->stage_grid = std::max(1, std::min(ctx->n_sm * ctx->stage_occ, (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sw, stage_wide_kernel, ST_THREADS, 0));
             ctx->stage_wide_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_sw), (nw + ST_WARPS - 1) / ST_WARPS));
         }
@@ -619,7 +632,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             if (!attr_set) { CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES)); attr_set = true; }
             int occ_p = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, PK_THREADS, PK_SMEM_BYTES));
-            ctx->pair_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_p), (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
+            ctx->pair_occ = std::max(1, occ_p);
+            ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
+            CK(ctx->d_rowdone.ensure(sizeof(unsigned) * (size_t)std::max(1, nf)));
         }
         CK(cudaStreamSynchronize(st));                       // tasks / wide_list are stack vectors
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
@@ -734,13 +749,14 @@ int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *max
     return BAGPU_OK;
 }
 
-int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr) {
+int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr, cudaStream_t stream = nullptr) {
+    if (!stream) stream = ctx->stream;
     static const bool no_cluster = getenv("BAGPU_NO_CLUSTER") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = grid; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(grid); cfg.stream = ctx->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
     if (maxr > 0) {
         cfg.blockDim = dim3(CB_THREADS);
         cfg.dynamicSmemBytes = chol_band_smem(a.n, maxr);
@@ -754,7 +770,7 @@ int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr) {
         return BAGPU_OK;
     }
     void *args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel<false>, dim3(grid), dim3(CH_THREADS), args, chol_dyn_smem(a.n), ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void *)chol_solve_kernel<false>, dim3(grid), dim3(CH_THREADS), args, chol_dyn_smem(a.n), stream));
     return BAGPU_OK;
 }
 
@@ -798,6 +814,14 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (ctx->s_elems + 2 * (size_t)std::max(1, n)), st));
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
+            CK(cudaMemsetAsync(ctx->d_y.p, 0, sizeof(double) * (size_t)std::max(1, n), st));
+            // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
+            // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
+            static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr;
+            const bool overlap = !no_overlap && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
+            if (overlap) CK(cudaMemsetAsync(ctx->d_rowdone.p, 0, sizeof(unsigned) * (size_t)ctx->n_free, st));
+            CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
+            ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && !getenv("BAGPU_NO_TILES");
@@ -806,19 +830,32 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             {
                 ScopedEv ev(ctx, EV_BUILD);
                 if (tiled) {
+                    // the Cholesky cluster is queued BEFORE stage_kernel: it takes its SMs now or as soon as the stage drains, in either
+                    // case ahead of pair_kernel; stage and pair leave those SMs alone (persistent grids sized for the rest)
+                    if (overlap) {
+                        ca.row_done = ctx->d_rowdone.as<unsigned>(); ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1;
+                        CK(cudaEventRecord(ctx->ev_fork, st));
+                        CK(cudaStreamWaitEvent(ctx->stream_chol, ctx->ev_fork, 0));
+                        { ScopedEv evc(ctx, EV_LINSOLVE, ctx->stream_chol); int rcc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, ctx->stream_chol); if (rcc) return rcc; }
+                        CK(cudaEventRecord(ctx->ev_join, ctx->stream_chol));
+                        ctx->tm.total_launches++;
+                    }
+                    const int sm_avail = overlap ? std::max(1, ctx->n_sm - ctx->chol_grid) : ctx->n_sm;
+                    const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
                     SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.fail = ctx->d_fail.as<int>();
-                    stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
-                    n_part_b = ctx->stage_grid;
+                    stage_kernel<<<sgrid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
+                    n_part_b = sgrid;
                     if (ctx->n_wide > 0) {             // landmarks with more than 32 observations: warp = landmark
                         StageArgs SW = SA; SW.part_chi2 = part_chi_w;
                         stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
                         have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
                     }
                     if (ctx->n_items > 0) {
-                        PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
+                        PairArgs PA; PA.row_done = overlap ? ctx->d_rowdone.as<unsigned>() : nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                         PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
-                        pair_kernel<<<ctx->pair_grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+                        const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
+                        pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
                         ctx->tm.total_launches++;
                     }
                 } else {
@@ -845,9 +882,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             ctx->tm.total_launches++;
             ctx->tm.edge_linearisations += n_active;
             int rc = all_reduce_sum(ctx, S, ctx->s_elems + 2 * (size_t)std::max(1, n)); if (rc) return rc;
-            if (n > 0) {
-                CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
-                ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
+            if (overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            else if (n > 0) {
                 { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr); if (rc) return rc; }
                 ctx->tm.total_launches++;
             }
@@ -1190,6 +1226,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemcpyAsync(dS.p, hS.data(), 8 * s_elems, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(db.p, b, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(dz.p, 0, 8 * (size_t)n, st));
+    CK(cudaMemsetAsync(dy.p, 0, 8 * (size_t)n, st));
     CK(cudaMemsetAsync(df.p, 0, 16, st));
     CK(cudaMemcpyAsync(dc.p, col_end, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     int tgrid = 1, tmaxr = 0;

@@ -39,6 +39,10 @@ struct CholArgs {
     double *x;                // [n] out
     int *fail;                // set to 1 on a non-positive pivot
     long long *prof;          // optional [8] cycle counters (potrf, trsm, sync1, writeback+y, update, sync2, backward)
+    // chol_band_kernel running BESIDE pair_kernel (single GPU): block column c is read once every work item of the camera
+    // rows it covers has been accumulated. row_done[a] counts finished items of row a, item_off[a * bw1] is the first item
+    // of row a in the plan. nullptr: the system is complete at launch.
+    const unsigned *row_done = nullptr; const unsigned *item_off = nullptr; int bw1 = 0;
 };
 
 // One warp factors the 32x32 SPD block in shared memory (Ld[r][c], lower part), 8 columns at a time:
@@ -361,6 +365,11 @@ __device__ __forceinline__ int ld_acquire_cluster(const int *p) {
     asm volatile("ld.acquire.cluster.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
@@ -501,11 +510,20 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
     for (int q = 0; q < 24; q++) pc[q] = 0;
 #define BT(i) do { if (a.prof) { t1 = clock64(); pc[i] += t1 - t0; t0 = t1; } } while (0)
     if (tid == 0) { s_fail = 0; s_flag = 0; }
-    for (int j = o * CB_THREADS + tid; j < n; j += NC * CB_THREADS) a.y[j] = a.bp[j] + a.bs[j];
+    // a.y (zeroed by the host) accumulates the forward-substitution updates; bp + bs join when a panel is solved
 
     // block column c of (S + lambda I) -> Cb (rows p0 .. rend, lower part; the strict upper part of the diagonal block = 0)
     auto load_block = [&](int c) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+        if (a.row_done) {                                  // wait for the camera rows of this block column (pair_kernel)
+            const int a0 = p0 / 6, a1 = (p0 + nb - 1) / 6;
+            if (tid <= a1 - a0) {
+                const int cam = a0 + tid;
+                const unsigned need = a.item_off[(size_t)(cam + 1) * a.bw1] - a.item_off[(size_t)cam * a.bw1];
+                while (ld_acquire_gpu(a.row_done + cam) < need) __nanosleep(100);
+            }
+            __syncthreads();
+        }
         const int R = rend_of(c) - p0 + 1;
         for (int j = warp; j < CH_NB; j += CB_WARPS) {
             const double *col = S + (size_t)(p0 + j) * ld + p0;
@@ -566,7 +584,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
             if (warp == CB_WARPS - 1) {
                 // forward substitution rides along: y_p = L11^{-1} y_p
                 const double di = invd[lane];
-                double v = (lane < nb) ? __ldcg(a.y + p0 + lane) * di : 0.0;
+                double v = (lane < nb) ? (__ldcg(a.bp + p0 + lane) + __ldcg(a.bs + p0 + lane) + __ldcg(a.y + p0 + lane)) * di : 0.0;
 #pragma unroll
                 for (int k = 0; k < CH_NB - 1; k++) {
                     const double yk = __shfl_sync(0xffffffffu, v, k);

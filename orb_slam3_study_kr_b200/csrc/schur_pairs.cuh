@@ -281,6 +281,7 @@ struct PairArgs {
     const int2 *entries;
     const double *Z, *Dr;
     double *S; int ld; double *bp, *bs;
+    unsigned *row_done;           // optional: finished items per camera row (chol_band_kernel runs beside this kernel)
 };
 
 // acc (6x6, row-major) += Z_x Z_y^T
@@ -358,6 +359,11 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
                 else atomicAdd(P.bs + 6 * I.a + (o - 27), s);
             }
             __syncwarp();
+        }
+        if (P.row_done) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.row_done + I.a, 1u);
         }
     }
 }
