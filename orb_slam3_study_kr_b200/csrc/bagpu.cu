@@ -123,7 +123,7 @@ struct bagpu_ctx {
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_widelist, d_tasks;
-    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone;
+    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone;
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, parts_stride = 1;
     int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
     size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
@@ -306,7 +306,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
                       &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_Z, &ctx->d_Dr, &ctx->d_entries, &ctx->d_items, &ctx->d_pk_keys, &ctx->d_pk_keys2, &ctx->d_pk_vals,
-                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp, &ctx->d_rowdone,
+                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp, &ctx->d_rowdone, &ctx->d_part, &ctx->d_blkdone,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -628,6 +628,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 CK(cudaGetLastError());
             }
             CK(ctx->d_Z.ensure(sizeof(double) * ZR_STRIDE * ne)); CK(ctx->d_Dr.ensure(sizeof(double) * DR_STRIDE * ne));
+            CK(ctx->d_part.ensure(sizeof(double) * PK_PART * (size_t)std::max(1, ctx->n_items)));
+            CK(ctx->d_blkdone.ensure(sizeof(unsigned) * ((size_t)nblk + 1)));
+            CK(cudaMemsetAsync(ctx->d_blkdone.p, 0, sizeof(unsigned) * ((size_t)nblk + 1), st));
             static bool attr_set = false;
             if (!attr_set) { CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES)); attr_set = true; }
             int occ_p = 0;
@@ -647,7 +650,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
-    ctx->parts_stride = std::max(std::max(std::max(ctx->build_grid, ctx->stage_grid), ctx->stage_wide_grid), ctx->upd_grid);
+    ctx->parts_stride = std::max(std::max(ctx->build_grid, ctx->stage_grid + ctx->stage_wide_grid), ctx->upd_grid);
     CK(ctx->d_parts.ensure(sizeof(double) * 7 * (size_t)ctx->parts_stride));
     CK(ctx->d_status.ensure(sizeof(double) * 32));
     CK(ctx->d_fail.ensure(sizeof(int) * 4));
@@ -794,12 +797,34 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         if (it == 0) {
             // computeLambdaInit: tau * max diagonal of Hpp and Hll (optimization_algorithm_levenberg.cpp:171-185)
             CK(cudaMemsetAsync(hpp, 0, sizeof(double) * std::max(1, n), st));
-            BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
-            O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
-            { ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O); }
+            int n_part0 = G;
+            if (n > 0 && ctx->n_items > 0 && !getenv("BAGPU_NO_TILES")) {
+                // the same stage / pair kernels as the trials (fixed summation order): Dr records, then the diagonal blocks only
+                ScopedEv ev(ctx, EV_BUILD);
+                StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
+                SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = 1.0; SA.part_chi2 = part_chi_b; SA.part_maxdiag = part_max;
+                SA.fail = ctx->d_fail.as<int>();
+                stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
+                n_part0 = ctx->stage_grid;
+                if (ctx->n_wide > 0) {
+                    StageArgs SW = SA; SW.part_chi2 = part_chi_b + ctx->stage_grid; SW.part_maxdiag = part_max + ctx->stage_grid;
+                    stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
+                    n_part0 += ctx->stage_wide_grid; ctx->tm.total_launches++;
+                }
+                PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
+                PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
+                PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1;
+                PA.row_done = nullptr; PA.hpp_diag = hpp;
+                pair_kernel<<<ctx->pair_grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+                ctx->tm.total_launches++;
+            } else {
+                BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
+                O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
+                ScopedEv ev(ctx, EV_BUILD); build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O);
+            }
             ctx->tm.total_launches++;
             int rc = all_reduce_sum(ctx, hpp, std::max(1, n)); if (rc) return rc;
-            reduce_partials_kernel<<<1, 256, 0, st>>>(G, part_chi_b, nullptr, part_max, nullptr, hpp, n, dstat);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part0, part_chi_b, nullptr, part_max, nullptr, hpp, n, dstat);
             ctx->tm.total_launches++;
             if (ctx->world > 1) { rc = all_reduce_sum(ctx, dstat, 1); if (rc) return rc; rc = all_reduce_max(ctx, dstat + 2, 1); if (rc) return rc; }
             double h[3];
@@ -843,7 +868,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     const int sm_avail = overlap ? std::max(1, ctx->n_sm - ctx->chol_grid) : ctx->n_sm;
                     const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
-                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.fail = ctx->d_fail.as<int>();
+                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
                     stage_kernel<<<sgrid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                     n_part_b = sgrid;
                     if (ctx->n_wide > 0) {             // landmarks with more than 32 observations: warp = landmark
@@ -852,7 +877,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
                     }
                     if (ctx->n_items > 0) {
-                        PairArgs PA; PA.row_done = overlap ? ctx->d_rowdone.as<unsigned>() : nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
+                        PairArgs PA; PA.row_done = overlap ? ctx->d_rowdone.as<unsigned>() : nullptr;
+                        PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1; PA.hpp_diag = nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                         PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
                         pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);

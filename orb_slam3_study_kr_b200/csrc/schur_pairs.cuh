@@ -19,15 +19,25 @@
 #pragma once
 #include "ba_kernels.cuh"
 
-#define ZR_STRIDE 18
-#define DR_STRIDE 34
-#define PK_CHUNK 512                       // entries per work item
+#define ZR_STRIDE 20                       // 18 used: 160-byte records = five 32-byte sectors, one 256-bit access each
+#define DR_STRIDE 36                       // 33 used: nine sectors
+#ifndef PK_CHUNK
+#define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
+#endif
 #define PK_THREADS 128
 #define PK_WARPS (PK_THREADS / 32)
 #define PK_RED_LD 33
 #define PK_SMEM_BYTES (PK_WARPS * 36 * PK_RED_LD * 8)
 
-struct PairItem { int a, b, begin, end; };
+struct PairItem { int a, b, begin, end, first, nit; };   // [begin, end) entries; the block's items are first .. first + nit - 1
+
+// 256-bit global accesses (sm_100a): one lane moves one whole 32-byte sector per instruction
+BA_DEV void ldg256(const double *p, double *v) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+BA_DEV void stg256(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // plan (upload): observations are sorted landmark-major / pose-ascending, free-pose indices are monotone in the pose index,
@@ -86,6 +96,7 @@ __global__ void pair_item_fill_kernel(int nblk, int bw1, const unsigned *__restr
     unsigned io = item_off[i];
     for (unsigned c = 0; c < cnt; c += PK_CHUNK) {
         PairItem I; I.a = a; I.b = b; I.begin = (int)(off + c); I.end = (int)(off + min(cnt, c + PK_CHUNK));
+        I.first = (int)item_off[i]; I.nit = (int)((cnt + PK_CHUNK - 1) / PK_CHUNK);
         items[io++] = I;
     }
 }
@@ -134,9 +145,8 @@ BA_DEV void lane_hll(const LaneEdge &E, double *r) {
 BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *__restrict__ Zp, double *__restrict__ Dp) {
     const bool act = E.valid;
     const double *A = E.L.A, *B = E.L.B;
-    double2 *zo = reinterpret_cast<double2 *>(Zp + ZR_STRIDE * e);
-    double2 *dout = reinterpret_cast<double2 *>(Dp + DR_STRIDE * e);
-    double z[18], bs[6];
+    double *zo = Zp + ZR_STRIDE * e, *dout = Dp + DR_STRIDE * e;
+    double z[ZR_STRIDE], bs[6];
 #pragma unroll
     for (int a = 0; a < 6; a++) {
         const double w0 = act ? E.wgt * (B[a] * A[0] + B[6 + a] * A[3] + B[12 + a] * A[6]) : 0.0;
@@ -148,8 +158,9 @@ BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *_
         z[3 * a] = z0; z[3 * a + 1] = z1; z[3 * a + 2] = z2;
         bs[a] = -(z0 * F.c0 + z1 * F.c1 + z2 * F.c2);
     }
+    z[18] = z[19] = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) zo[i] = make_double2(z[2 * i], z[2 * i + 1]);
+    for (int i = 0; i < ZR_STRIDE / 4; i++) stg256(zo + 4 * i, z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
     double d[DR_STRIDE];
     int p = 0;
 #pragma unroll
@@ -160,9 +171,9 @@ BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *_
     for (int a = 0; a < 6; a++) d[21 + a] = act ? (B[a] * E.g0 + B[6 + a] * E.g1 + B[12 + a] * E.g2) : 0.0;
 #pragma unroll
     for (int a = 0; a < 6; a++) d[27 + a] = bs[a];
-    d[33] = 0.0;
+    d[33] = d[34] = d[35] = 0.0;
 #pragma unroll
-    for (int i = 0; i < DR_STRIDE / 2; i++) dout[i] = make_double2(d[2 * i], d[2 * i + 1]);
+    for (int i = 0; i < DR_STRIDE / 4; i++) stg256(dout + 4 * i, d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
 }
 
 struct StageArgs {
@@ -172,13 +183,14 @@ struct StageArgs {
     double *Z, *Dr;
     double lambda;
     double *part_chi2;            // [gridDim.x]
+    double *part_maxdiag;         // optional [gridDim.x]: max |Hll diagonal| (computeLambdaInit)
     int *fail;
 };
 
 __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
-    __shared__ double s_chi[ST_WARPS];
+    __shared__ double s_chi[ST_WARPS], s_max[ST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double chi_acc = 0.0;
+    double chi_acc = 0.0, max_acc = 0.0;
     bool bad = false;
     for (int t = blockIdx.x * ST_WARPS + warp; t < S.n_tasks; t += gridDim.x * ST_WARPS) {
         const int2 tk = S.tasks[t];
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, con
         }
 #pragma unroll
         for (int i = 0; i < 10; i++) r[i] = __shfl_sync(0xffffffffu, r[i], head);
-        if (in && lane == head) chi_acc += r[9];
+        if (in && lane == head) { chi_acc += r[9]; max_acc = fmax(max_acc, fmax(fabs(r[0]), fmax(fabs(r[3]), fabs(r[5])))); }
         LmFactor F;
         const bool ok = lm_factor(r, S.lambda, F);
         if (in && !ok) bad = true;
@@ -220,20 +232,22 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, con
     }
     if (bad) atomicOr(S.fail, 1);
     chi_acc = warp_allsum(chi_acc);
-    if (lane == 0) s_chi[warp] = chi_acc;
+    max_acc = warp_allmax(max_acc);
+    if (lane == 0) { s_chi[warp] = chi_acc; s_max[warp] = max_acc; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double c = 0.0;
-        for (int w = 0; w < ST_WARPS; w++) c += s_chi[w];
+        double c = 0.0, m = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) { c += s_chi[w]; m = fmax(m, s_max[w]); }
         S.part_chi2[blockIdx.x] = c;
+        if (S.part_maxdiag) S.part_maxdiag[blockIdx.x] = m;
     }
 }
 
 // the same for landmarks with more than 32 observations: warp = landmark, two passes over its chunks
 __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
-    __shared__ double s_chi[ST_WARPS];
+    __shared__ double s_chi[ST_WARPS], s_max[ST_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double chi_acc = 0.0;
+    double chi_acc = 0.0, max_acc = 0.0;
     bool bad = false;
     for (int jj = blockIdx.x * ST_WARPS + warp; jj < S.n_list; jj += gridDim.x * ST_WARPS) {
         const int j = __ldg(S.lm_list + jj);
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D
 #pragma unroll
         for (int i = 0; i < 10; i++) acc[i] = warp_allsum(acc[i]);
         chi_acc += acc[9];
+        max_acc = fmax(max_acc, fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5]))));
         LmFactor F;
         if (!lm_factor(acc, S.lambda, F)) bad = true;
         for (int c = 0; c < nchunk; c++) {
@@ -265,34 +280,38 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D
         }
     }
     if (bad) atomicOr(S.fail, 1);
-    if (lane == 0) s_chi[warp] = chi_acc;          // warp_allsum left the same value in every lane
+    if (lane == 0) { s_chi[warp] = chi_acc; s_max[warp] = max_acc; }          // warp_allsum left the same value in every lane
     __syncthreads();
     if (threadIdx.x == 0) {
-        double c = 0.0;
-        for (int w = 0; w < ST_WARPS; w++) c += s_chi[w];
+        double c = 0.0, m = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) { c += s_chi[w]; m = fmax(m, s_max[w]); }
         S.part_chi2[blockIdx.x] = c;
+        if (S.part_maxdiag) S.part_maxdiag[blockIdx.x] = m;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pair
+#define PK_PART 72                         // doubles per item in the partial buffer: Z Z^T (36) | Dr sums (33) | pad
 struct PairArgs {
     const PairItem *items; int n_items;
     const int2 *entries;
     const double *Z, *Dr;
     double *S; int ld; double *bp, *bs;
+    double *part;                 // [n_items][PK_PART] partial sums of blocks cut into several items
+    unsigned *blk_done; int bw1;  // finished items per block (never reset: the last finisher is the one that completes a multiple of nit)
     unsigned *row_done;           // optional: finished items per camera row (chol_band_kernel runs beside this kernel)
+    double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit (only the Dr sums of the diagonal blocks)
 };
 
 // acc (6x6, row-major) += Z_x Z_y^T
 BA_DEV void pair_accumulate(const double *__restrict__ Z, int ex, int ey, double *acc) {
-    const double2 *px = reinterpret_cast<const double2 *>(Z + ZR_STRIDE * (size_t)ex);
-    const double2 *py = reinterpret_cast<const double2 *>(Z + ZR_STRIDE * (size_t)ey);
-    double x[18], y[18];
+    const double *px = Z + ZR_STRIDE * (size_t)ex, *py = Z + ZR_STRIDE * (size_t)ey;
+    double x[ZR_STRIDE], y[ZR_STRIDE];
 #pragma unroll
-    for (int i = 0; i < 9; i++) { const double2 v = __ldg(py + i); y[2 * i] = v.x; y[2 * i + 1] = v.y; }
+    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(py + 4 * i, y + 4 * i);
 #pragma unroll
-    for (int i = 0; i < 9; i++) { const double2 v = __ldg(px + i); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(px + 4 * i, x + 4 * i);
 #pragma unroll
     for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -307,8 +326,10 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
     for (int it = blockIdx.x * PK_WARPS + warp; it < P.n_items; it += gridDim.x * PK_WARPS) {
         const PairItem I = P.items[it];
         const bool diag = I.a == I.b;
-        double *Sblk = P.S + (size_t)(6 * I.a) * P.ld + 6 * I.b;
-        {
+        if (P.hpp_diag && !diag) continue;
+        // ---- this item's share of sum Z_a Z_b^T: lane l ends with elements l and l + 32 (sz0, sz1)
+        double sz0 = 0.0, sz1 = 0.0, sd0 = 0.0, sd1 = 0.0;
+        if (!P.hpp_diag) {
             double acc[36];
 #pragma unroll
             for (int i = 0; i < 36; i++) acc[i] = 0.0;
@@ -319,17 +340,15 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
             }
 #pragma unroll
             for (int i = 0; i < 36; i++) red[i * PK_RED_LD + lane] = acc[i];
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int o = lane; o < 36; o += 32) {
-            double s = 0.0;
+            __syncwarp();
 #pragma unroll 8
-            for (int l = 0; l < 32; l++) s += red[o * PK_RED_LD + l];
-            const int r = o / 6, c = o - 6 * r;
-            if ((!diag || c >= r) && s != 0.0) atomicAdd(Sblk + (size_t)r * P.ld + c, -s);
+            for (int l = 0; l < 32; l++) sz0 += red[lane * PK_RED_LD + l];
+            if (lane < 4) {
+#pragma unroll 8
+                for (int l = 0; l < 32; l++) sz1 += red[(32 + lane) * PK_RED_LD + l];
+            }
+            __syncwarp();
         }
-        __syncwarp();
         if (diag) {
             // Hpp, bp, bs of camera a: sum of the Dr records of its observations (the (e, e) entries)
             double d[DR_STRIDE];
@@ -338,32 +357,79 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
             for (int i = I.begin + lane; i < I.end; i += 32) {
                 const int2 en = __ldg(P.entries + i);
                 if (en.x != en.y) continue;
-                const double2 *pd = reinterpret_cast<const double2 *>(P.Dr + DR_STRIDE * (size_t)en.x);
+                const double *pd = P.Dr + DR_STRIDE * (size_t)en.x;
 #pragma unroll
-                for (int q = 0; q < DR_STRIDE / 2; q++) { const double2 v = __ldg(pd + q); d[2 * q] += v.x; d[2 * q + 1] += v.y; }
+                for (int q = 0; q < DR_STRIDE / 4; q++) { double v[4]; ldg256(pd + 4 * q, v); d[4 * q] += v[0]; d[4 * q + 1] += v[1]; d[4 * q + 2] += v[2]; d[4 * q + 3] += v[3]; }
             }
 #pragma unroll
-            for (int i = 0; i < DR_STRIDE - 1; i++) red[i * PK_RED_LD + lane] = d[i];
+            for (int i = 0; i < 33; i++) red[i * PK_RED_LD + lane] = d[i];
             __syncwarp();
-#pragma unroll 1
-            for (int o = lane; o < DR_STRIDE - 1; o += 32) {
-                double s = 0.0;
 #pragma unroll 8
-                for (int l = 0; l < 32; l++) s += red[o * PK_RED_LD + l];
-                if (s == 0.0) continue;
-                if (o < 21) {
-                    int r = 0, t = o;
-                    while (t >= 6 - r) { t -= 6 - r; r++; }
-                    atomicAdd(Sblk + (size_t)r * P.ld + r + t, s);
-                } else if (o < 27) atomicAdd(P.bp + 6 * I.a + (o - 21), s);
-                else atomicAdd(P.bs + 6 * I.a + (o - 27), s);
+            for (int l = 0; l < 32; l++) sd0 += red[lane * PK_RED_LD + l];
+            if (lane == 0) {
+#pragma unroll 8
+                for (int l = 0; l < 32; l++) sd1 += red[32 * PK_RED_LD + l];
             }
             __syncwarp();
+        }
+        // ---- blocks cut into several items: partials go to memory, the LAST finisher adds them up in item order, so the
+        // reduced system does not depend on which warp ran when (one total per block reaches S)
+        if (I.nit > 1) {
+            double *mine = P.part + (size_t)it * PK_PART;
+            __stcg(mine + lane, sz0);
+            if (lane < 4) __stcg(mine + 32 + lane, sz1);
+            if (diag) { __stcg(mine + 36 + lane, sd0); if (lane == 0) __stcg(mine + 68, sd1); }
+            __threadfence();
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(P.blk_done + (size_t)I.a * P.bw1 + (I.b - I.a), 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if ((prev + 1u) % (unsigned)I.nit != 0u) continue;                       // somebody else finishes the block
+            __threadfence();
+            sz0 = sz1 = sd0 = sd1 = 0.0;
+            for (int k = 0; k < I.nit; k++) {
+                const double *pk = P.part + (size_t)(I.first + k) * PK_PART;
+                sz0 += __ldcg(pk + lane);
+                if (lane < 4) sz1 += __ldcg(pk + 32 + lane);
+                if (diag) { sd0 += __ldcg(pk + 36 + lane); if (lane == 0) sd1 += __ldcg(pk + 68); }
+            }
+        }
+        if (P.hpp_diag) {                                                            // computeLambdaInit: diagonal of Hpp only
+            int r = 0, t = lane;
+            while (r < 6 && t >= 6 - r) { t -= 6 - r; r++; }
+            if (lane < 21 && t == 0) P.hpp_diag[6 * I.a + r] = sd0;
+            continue;
+        }
+        // ---- the block's total: at most two adds per element of S onto the zeroed system (exact in any order)
+        double *Sblk = P.S + (size_t)(6 * I.a) * P.ld + 6 * I.b;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int o = lane + 32 * h;
+            const double s = h ? sz1 : sz0;
+            if (o < 36) {
+                const int r = o / 6, c = o - 6 * r;
+                if ((!diag || c >= r) && s != 0.0) atomicAdd(Sblk + (size_t)r * P.ld + c, -s);
+            }
+        }
+        if (diag) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int o = lane + 32 * h;
+                const double s = h ? sd1 : sd0;
+                if (o < 33 && s != 0.0) {
+                    if (o < 21) {
+                        int r = 0, t = o;
+                        while (t >= 6 - r) { t -= 6 - r; r++; }
+                        atomicAdd(Sblk + (size_t)r * P.ld + r + t, s);
+                    } else if (o < 27) atomicAdd(P.bp + 6 * I.a + (o - 21), s);
+                    else atomicAdd(P.bs + 6 * I.a + (o - 27), s);
+                }
+            }
         }
         if (P.row_done) {
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicAdd(P.row_done + I.a, 1u);
+            if (lane == 0) atomicAdd(P.row_done + I.a, (unsigned)I.nit);
         }
     }
 }
