@@ -13,9 +13,11 @@ A step = one Optimizer::GlobalBundleAdjustemnt call = optimize(20) from the init
           HBM, timed with CUDA events on the library's stream, max over ranks.
   e2e     the same metric through the reference-facing C-ABI call bagpu_solve_ba with HOST buffers: H2D of the whole
           problem, solve, D2H of poses / points / per-edge chi2 / flags inside the timed region.
-  roofline  the linearise+Schur pass (stage_kernel + apply_kernel; build_kernel for the few wide landmarks), the dominant
-          kernel group: algorithmic bytes per pass / mean pass duration (CUDA events around every pass in the timed
-          region, on the library's stream) against the measured HBM copy bandwidth.
+  roofline  the linearise+Schur pass (stage_kernel + pair_kernel), the dominant kernel group of the library stream:
+          algorithmic bytes per pass / mean pass duration (CUDA events around every pass in the timed region, on the
+          library's stream) against the measured HBM copy bandwidth. On one GPU the band Cholesky runs BESIDE pair_kernel
+          on a second stream, so the `kernels` shares overlap and sum to more than 1.
+  local_ba  secondary lines (1 GPU): configs 1-3 through bagpu_solve_ba and the 1000-frame PoseOptimization batch, end to end.
 """
 from __future__ import annotations
 
@@ -184,6 +186,43 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- secondary lines: local BA, pose batch (1 GPU)
+def local_ba_lines(ctx, l2_flush, reps: int = 5):
+    """BASELINE.json configs 1-3 through bagpu_solve_ba / bagpu_pose_opt_batch with host buffers (end to end, wall clock):
+    Optimizer::LocalBundleAdjustment (LocalMapping schedule: optimize(10), robust) and batched Optimizer::PoseOptimization."""
+    from orb_slam3_study_kr_b200 import synthetic
+    from orb_slam3_study_kr_b200.problem import schedule_local_ba
+    out = {}
+    s = schedule_local_ba()
+    for cfg in (1, 2, 3):
+        p = synthetic.config(cfg)
+        ctx.pin_problem(p)
+        buf = ctx.alloc_result(p, s)
+        ctx.solve_ba(p, s, into=buf)
+        ts, passes, iters = [], 0, 0
+        for _ in range(reps):
+            l2_flush()
+            t0 = time.perf_counter()
+            ctx.solve_ba(p, s, into=buf)
+            ts.append(time.perf_counter() - t0)
+            t = ctx.timing()
+            passes, iters = t["edge_linearisations"] + t["edge_evaluations"], t["lm_iterations"]
+        ms = 1e3 * float(np.median(ts))
+        out["C%d" % cfg] = {"observations": int(p.n_obs), "free_poses": int(p.n_free), "points": int(p.n_points), "e2e_ms_per_call": ms,
+                            "lm_iterations": int(iters), "lm_iters_per_s": iters / (ms * 1e-3), "edge_passes_per_s": passes / (ms * 1e-3)}
+    b = synthetic.make_pose_batch(n_frames=1000, n_matches=300)
+    ctx.pose_opt_batch(b)
+    ts = []
+    for _ in range(reps):
+        l2_flush()
+        t0 = time.perf_counter()
+        ctx.pose_opt_batch(b)
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.median(ts))
+    out["pose_opt_batch"] = {"frames": 1000, "edges": int(b.n_obs), "e2e_ms_per_call": ms, "frames_per_s": 1000 / (ms * 1e-3)}
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args, rank: int, world: int, local_rank: int):
     import torch
@@ -277,13 +316,15 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(acc["total_launches"]),
                 "clocks": clk.summary(),
-                "roofline": {"kernel": "linearise+Schur pass: stage_kernel + apply_kernel (+ build_kernel for wide landmarks)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "linearise+Schur pass: stage_kernel + pair_kernel (CUDA events around the two launches on the library stream; the band Cholesky runs beside pair_kernel on its own stream)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": build_avg_ms,
                              "launches": int(acc["build_launches"])},
                 "kernels": {"build_ms_per_step": acc["build_ms"] / args.steps, "linsolve_ms_per_step": acc["linsolve_ms"] / args.steps,
                             "update_ms_per_step": acc["update_ms"] / args.steps,
                             "share_of_step": {k: acc[k + "_ms"] / dev_ms for k in ("build", "linsolve", "update")}}}
+        if world == 1 and not args.no_local:
+            line["local_ba"] = local_ba_lines(ctx, l2_flush)
         # CPU baseline beside it (rank 0, N=1 only): a bounded sample of the same map on one host core
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ba_ref
@@ -307,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="bagpu", choices=["bagpu", "reference"])
     ap.add_argument("--ref-iters", type=int, default=4, help="LM iterations per CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-local", action="store_true", help="skip the secondary local-BA / pose-batch lines")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -842,7 +842,10 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(ctx->d_y.p, 0, sizeof(double) * (size_t)std::max(1, n), st));
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
-            static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr;
+            static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr ||
+                                           // tools that serialise kernel launches (ncu, compute-sanitizer) would leave the Cholesky spinning
+                                           getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                                           getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr || getenv("CUDA_LAUNCH_BLOCKING") != nullptr;
             const bool overlap = !no_overlap && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
             if (overlap) CK(cudaMemsetAsync(ctx->d_rowdone.p, 0, sizeof(unsigned) * (size_t)ctx->n_free, st));
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;

@@ -520,7 +520,15 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
             if (tid <= a1 - a0) {
                 const int cam = a0 + tid;
                 const unsigned need = a.item_off[(size_t)(cam + 1) * a.bw1] - a.item_off[(size_t)cam * a.bw1];
-                while (ld_acquire_gpu(a.row_done + cam) < need) __nanosleep(100);
+                // pair_kernel runs beside this kernel; if it cannot (a profiler serialising kernels, a starved device) give up after
+                // 2 s and report a failed solve instead of hanging: the LM loop treats it as a rejected trial
+                unsigned long long t_start = 0, t_now = 0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+                while (ld_acquire_gpu(a.row_done + cam) < need) {
+                    __nanosleep(100);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                    if (t_now - t_start > 2000000000ull) { atomicExch(a.fail, 1); break; }
+                }
             }
             __syncthreads();
         }
