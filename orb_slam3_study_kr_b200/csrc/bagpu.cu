@@ -110,6 +110,15 @@ struct bagpu_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_chol = nullptr;    // the band Cholesky runs beside pair_kernel on its own (high-priority) stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_chol2 = nullptr;   // second half of the two-way factorisation
+    cudaEvent_t ev_tw[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct TwoWay {                        // band factored from both ends towards a separator block M
+        bool on = false;
+        int k = 0, rT = 0, n1 = 0, n2 = 0, nM = 0, ldM = 0;
+        int grid1 = 1, maxr1 = 0, grid2 = 1, maxr2 = 0, gridM = 1, maxrM = 0;
+        size_t s2_elems = 0, sM_elems = 0;
+    } tw;
+    DevBuf d_colend1, d_colend2, d_colendM, d_y2, d_SM, d_rhsM, d_zeroM, d_yM, d_xM, d_rowpos, d_rowofpos;
     char err[512] = {0};
     // ---- communicator (multi-GPU global BA)
     ncclComm_t comm = nullptr; int world = 1, rank = 0;
@@ -121,7 +130,7 @@ struct bagpu_ctx {
     DevBuf d_lm_ptr, d_o_pose, d_o_point, d_o_meta, d_o_u, d_o_v, d_o_ur, d_o_w, d_cams, d_rigs, d_hidx, d_perm;
     DevBuf d_raw8a, d_raw8b, d_raw16a, d_raw16b, d_rawd;     // raw upload staging on the device
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
-    DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | hpp_diag (n)] contiguous (one all-reduce)
+    DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | S2 (two-way: mirrored lower half) | hpp_diag (n)]; S .. S2 contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_widelist, d_tasks;
     DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone;
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, parts_stride = 1;
@@ -211,6 +220,31 @@ __global__ void gather_perm_kernel(int64_t n, const int *__restrict__ perm, cons
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[perm[i]];
 }
+// ---- two-way band factorisation: glue between the two half-systems and the separator block M (rows rT .. rT + nM - 1)
+// S_M = S1[M,M] + mirror(S2[M,M]) (partial Schur complements, no lambda), rhs_M = b_p + b_s + forward updates of both halves
+__global__ void tw_merge_kernel(int nM, int rT, int n, int ld, const double *__restrict__ S1, const double *__restrict__ S2,
+                                const double *__restrict__ bp, const double *__restrict__ bs, const double *__restrict__ y1,
+                                const double *__restrict__ y2, double *SM, int ldM, double *rhsM) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nM * nM) return;
+    const int R = idx / nM, C = idx - R * nM;
+    if (C < R) return;
+    double v = 0.0;
+    if (C - R <= ld) {
+        const int Ro = rT + R, Co = rT + C;
+        v = S1[(size_t)Ro * ld + Co] + S2[(size_t)(n - 1 - Co) * ld + (n - 1 - Ro)];
+    }
+    SM[(size_t)R * ldM + C] = v;
+    if (R == C) { const int Ro = rT + R; rhsM[R] = bp[Ro] + bs[Ro] + y1[Ro] + y2[n - 1 - Ro]; }
+}
+// x_M into the final x and into the right-hand sides of the two backward substitutions
+__global__ void tw_scatter_kernel(int nM, int rT, int n, const double *__restrict__ xM, double *y1, double *y2, double *x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nM) return;
+    const int Ro = rT + k;
+    const double v = xM[k];
+    y1[Ro] = v; y2[n - 1 - Ro] = v; x[Ro] = v;
+}
 __global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, float *o) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = baf_atan2f(y[i], x[i]);
@@ -292,7 +326,24 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         if (cudaStreamCreateWithPriority(&ctx->stream_chol, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return BAGPU_ERR_CUDA; }
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&ctx->stream_chol2, cudaStreamNonBlocking, hi); }
+    for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->ev_tw[i], cudaEventDisableTiming);
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev_phase[i]);
+    {
+        // Load every kernel now. With CUDA's lazy module loading the FIRST launch of a kernel may synchronise the context; a
+        // launch that does so while the Cholesky clusters spin on pair_kernel's counters (pair_kernel not yet enqueued) would
+        // block the host until the watchdog fires.
+        cudaFuncAttributes fa;
+        const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
+                             (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel,
+                             (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel,
+                             (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel,
+                             (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
+                             (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
+                             (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
+                             (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel};
+        for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
+    }
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     *out = ctx;
     return BAGPU_OK;
@@ -314,6 +365,10 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     ctx->h_status.release(); ctx->h_stage.release();
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; i++) if (ctx->ev_phase[i]) cudaEventDestroy(ctx->ev_phase[i]);
+    for (int i = 0; i < 4; i++) if (ctx->ev_tw[i]) cudaEventDestroy(ctx->ev_tw[i]);
+    if (ctx->stream_chol2) { cudaStreamSynchronize(ctx->stream_chol2); cudaStreamDestroy(ctx->stream_chol2); }
+    { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
+      for (DevBuf *x : tb) x->release(); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaStreamSynchronize(ctx->stream_chol);
@@ -532,8 +587,66 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             band = std::max(band, rend - p0 + 1);            // ... and every column of a panel stores the panel's rows
         }
         ctx->ld = std::max(1, std::min(band - 1, n));        // band storage when it is narrower than the matrix
-        ctx->s_elems = (size_t)std::max(1, n) * (ctx->ld + 1) + 8;   // Lm(i,j) = S[j*ld + i], i in [j, j+band): last index (n-1)*(ld+1)
         { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid, &ctx->chol_maxr); if (rc2) return rc2; }
+        // --- two-way factorisation: rows [0, rT) from the top, rows [n - rT, n) from the bottom (mirrored), separator M between
+        ctx->tw = bagpu_ctx::TwoWay();
+        std::vector<int> ce1, ce2, ceM;
+        if (ctx->chol_maxr > 0 && !getenv("BAGPU_NO_TWOWAY") && !getenv("BAGPU_COMPARE") && !getenv("BAGPU_NO_TILES")) {
+            int band_rows = 1;
+            for (int j = 0; j < n; j++) band_rows = std::max(band_rows, std::min(n - 1, col_end[j]) - j + 1);
+            const int k = (n - band_rows - CH_NB) / (2 * CH_NB);
+            if (k >= 8) {
+                bagpu_ctx::TwoWay &T = ctx->tw;
+                T.k = k; T.rT = CH_NB * k; T.n1 = n - CH_NB * k; T.n2 = n - T.rT; T.nM = T.n1 - T.rT;
+                ce1.resize(T.n1); ce2.resize(T.n2); ceM.assign(T.nM, T.nM - 1);
+                for (int j = 0; j < T.n1; j++) ce1[j] = std::min(col_end[j], T.n1 - 1);
+                std::vector<int> first_row(n, 0);           // first row with a possibly-nonzero entry in column C of the upper triangle
+                { int c0 = 0; for (int R = 0; R < n; R++) { const int ce = std::min(n - 1, col_end[R]); for (; c0 <= ce; c0++) first_row[c0] = R; } }
+                for (int j = 0; j < T.n2; j++) ce2[j] = std::min(T.n2 - 1, n - 1 - first_row[n - 1 - j]);
+                auto metrics = [&](const std::vector<int> &ce, int nn, int &bnd, int &mb) {
+                    bnd = 1; mb = 0;
+                    for (int j = 0; j < nn; j++) bnd = std::max(bnd, ce[j] - j + 1);
+                    for (int p0 = 0; p0 < nn; p0 += CH_NB) {
+                        const int nb = std::min(CH_NB, nn - p0);
+                        const int rend = std::min(nn - 1, ce[p0 + nb - 1]);
+                        mb = std::max(mb, rend - (p0 + nb) + 1);
+                        bnd = std::max(bnd, rend - p0 + 1);
+                    }
+                };
+                int b1, mb1, b2, mb2, bM, mbM;
+                metrics(ce1, T.n1, b1, mb1); metrics(ce2, T.n2, b2, mb2); metrics(ceM, T.nM, bM, mbM);
+                ctx->ld = std::max(ctx->ld, std::max(1, std::min(std::max(b1, b2) - 1, n)));   // one row stride for S, S1 (= S) and S2
+                T.ldM = std::max(1, std::min(bM - 1, T.nM));
+                T.s2_elems = (size_t)T.n2 * (ctx->ld + 1) + 8; T.sM_elems = (size_t)T.nM * (T.ldM + 1) + 8;
+                int rc2 = chol_plan_grid(ctx, T.n1, mb1, &T.grid1, &T.maxr1); if (rc2) return rc2;
+                rc2 = chol_plan_grid(ctx, T.n2, mb2, &T.grid2, &T.maxr2); if (rc2) return rc2;
+                rc2 = chol_plan_grid(ctx, T.nM, mbM, &T.gridM, &T.maxrM); if (rc2) return rc2;
+                T.on = T.maxr1 > 0 && T.maxr2 > 0 && T.maxrM > 0 && T.grid1 + T.grid2 + 8 <= ctx->n_sm;
+            }
+        }
+        ctx->s_elems = (size_t)std::max(1, n) * (ctx->ld + 1) + 8;   // Lm(i,j) = S[j*ld + i], i in [j, j+band): last index (n-1)*(ld+1)
+        if (ctx->tw.on) {
+            const bagpu_ctx::TwoWay &T = ctx->tw;
+            CK(ctx->d_colend1.ensure(4 * (size_t)T.n1)); CK(ctx->d_colend2.ensure(4 * (size_t)T.n2)); CK(ctx->d_colendM.ensure(4 * (size_t)T.nM));
+            CK(ctx->d_y2.ensure(8 * (size_t)T.n2)); CK(ctx->d_SM.ensure(8 * T.sM_elems)); CK(ctx->d_rhsM.ensure(8 * (size_t)T.nM));
+            CK(ctx->d_zeroM.ensure(8 * (size_t)T.nM)); CK(ctx->d_yM.ensure(8 * (size_t)T.nM)); CK(ctx->d_xM.ensure(8 * (size_t)T.nM));
+            CK(cudaMemcpyAsync(ctx->d_colend1.p, ce1.data(), 4 * (size_t)T.n1, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_colend2.p, ce2.data(), 4 * (size_t)T.n2, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_colendM.p, ceM.data(), 4 * (size_t)T.nM, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(ctx->d_zeroM.p, 0, 8 * (size_t)T.nM, st));
+            if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] two-way: k=%d rT=%d n1=%d n2=%d nM=%d ld=%d ldM=%d grids %d/%d/%d maxr %d/%d/%d\n",
+                                               T.k, T.rT, T.n1, T.n2, T.nM, ctx->ld, T.ldM, T.grid1, T.grid2, T.gridM, T.maxr1, T.maxr2, T.maxrM);
+        }
+        {   // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
+            std::vector<int> row_pos(std::max(1, nf)), row_of_pos(std::max(1, nf));
+            if (ctx->tw.on) { int lo = 0, hi = nf - 1, p2 = 0; while (lo <= hi) { row_of_pos[p2++] = lo++; if (lo <= hi) row_of_pos[p2++] = hi--; } }
+            else for (int h = 0; h < nf; h++) row_of_pos[h] = h;
+            for (int q = 0; q < nf; q++) row_pos[row_of_pos[q]] = q;
+            CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
+            CK(cudaMemcpyAsync(ctx->d_rowpos.p, row_pos.data(), 4 * (size_t)std::max(1, nf), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_rowofpos.p, row_of_pos.data(), 4 * (size_t)std::max(1, nf), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
         const int occ_c = 0;
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d occ=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid, occ_c);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
@@ -590,7 +703,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaMemsetAsync(blkcnt, 0, 4 * ((size_t)nblk + 1), st));
             CK(cudaMemsetAsync(npairs + ne, 0, 4, st));
             pair_count_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
-                                                 bw1, npairs, blkcnt);
+                                                 ctx->d_rowpos.as<int>(), bw1, npairs, blkcnt);
             pair_item_count_kernel<<<grid_for(nblk + 1, 256), 256, 0, st>>>(nblk + 1, blkcnt, itemcnt);
             size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
             CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, npairs, pairoff, (int)(ne + 1), st));
@@ -614,7 +727,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 CK(ctx->d_pk_vals.ensure(8 * npr)); CK(ctx->d_entries.ensure(8 * npr));
                 CK(ctx->d_items.ensure(sizeof(PairItem) * (size_t)std::max(1, ctx->n_items)));
                 pair_gen_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
-                                                   bw1, pairoff, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_vals.as<int2>());
+                                                   ctx->d_rowpos.as<int>(), bw1, pairoff, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_vals.as<int2>());
                 int end_bit = 1;
                 while (end_bit < 32 && (1ll << end_bit) < nblk_ll) end_bit++;
                 static_assert(sizeof(unsigned long long) == sizeof(int2), "pair entry size");
@@ -624,7 +737,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 tmp = ctx->d_cubtmp.cap;
                 CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, tmp, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
                                                    ctx->d_pk_vals.as<unsigned long long>(), ctx->d_entries.as<unsigned long long>(), (int)npr, 0, end_bit, st));
-                pair_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, st>>>(nblk, bw1, blkoff, blkcnt, itemoff, ctx->d_items.as<PairItem>());
+                pair_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, st>>>(nblk, bw1, ctx->d_rowofpos.as<int>(), blkoff, blkcnt, itemoff, ctx->d_items.as<PairItem>());
                 CK(cudaGetLastError());
             }
             CK(ctx->d_Z.ensure(sizeof(double) * ZR_STRIDE * ne)); CK(ctx->d_Dr.ensure(sizeof(double) * DR_STRIDE * ne));
@@ -643,7 +756,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
                                            ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
-    CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n))));
+    CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n) + ctx->tw.s2_elems)));   // [S | bp | bs | S2 | hpp_diag]
     CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
     CK(ctx->d_y.ensure(sizeof(double) * (size_t)std::max(1, n)));
     CK(ctx->d_dinv.ensure(sizeof(double) * (size_t)std::max(1, n)));
@@ -782,7 +895,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
     const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid, PS = ctx->parts_stride;
     double *S = ctx->d_sys.as<double>();
-    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *hpp = bs + std::max(1, n);
+    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *S2 = bs + std::max(1, n), *hpp = S2 + ctx->tw.s2_elems;
+    const size_t sys_count = ctx->s_elems + 2 * (size_t)std::max(1, n) + ctx->tw.s2_elems;      // what a trial zeroes and all-reduces
     double *parts = ctx->d_parts.as<double>();
     double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS,
            *part_chi_uw = parts + 5 * PS, *part_scale_w = parts + 6 * PS;
@@ -814,7 +928,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                 PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
                 PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1;
-                PA.row_done = nullptr; PA.hpp_diag = hpp;
+                PA.row_done = nullptr; PA.hpp_diag = hpp; PA.S2 = nullptr; PA.n_tot = n; PA.n1 = n;
                 pair_kernel<<<ctx->pair_grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
                 ctx->tm.total_launches++;
             } else {
@@ -837,9 +951,10 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         bool first = true;
         do {
             // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
-            CK(cudaMemsetAsync(S, 0, sizeof(double) * (ctx->s_elems + 2 * (size_t)std::max(1, n)), st));
+            CK(cudaMemsetAsync(S, 0, sizeof(double) * sys_count, st));
             CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
             CK(cudaMemsetAsync(ctx->d_y.p, 0, sizeof(double) * (size_t)std::max(1, n), st));
+            if (ctx->tw.on) { CK(cudaMemsetAsync(ctx->d_y2.p, 0, sizeof(double) * (size_t)ctx->tw.n2, st)); CK(cudaMemsetAsync(ctx->d_yM.p, 0, sizeof(double) * (size_t)ctx->tw.nM, st)); }
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
             static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr ||
@@ -850,6 +965,35 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             if (overlap) CK(cudaMemsetAsync(ctx->d_rowdone.p, 0, sizeof(unsigned) * (size_t)ctx->n_free, st));
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
             ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
+            // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator
+            auto enqueue_solver = [&](cudaStream_t sc, bool waits) -> int {
+                if (waits) { ca.row_done = ctx->d_rowdone.as<unsigned>(); ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
+                if (!ctx->tw.on) { ctx->tm.total_launches++; return launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, sc); }
+                const bagpu_ctx::TwoWay &T = ctx->tw;
+                cudaStream_t s2 = ctx->stream_chol2;
+                CholArgs c1 = ca; c1.n = T.n1; c1.col_end = ctx->d_colend1.as<int>(); c1.p_stop = T.k;
+                CholArgs c2 = ca; c2.S = S2; c2.n = T.n2; c2.col_end = ctx->d_colend2.as<int>(); c2.y = ctx->d_y2.as<double>(); c2.p_stop = T.k;
+                c2.mirror_n = n; c2.wait_band = ld + 1;
+                CK(cudaEventRecord(ctx->ev_tw[0], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[0], 0));
+                int r = launch_chol(ctx, c1, T.grid1, T.maxr1, sc); if (r) return r;
+                r = launch_chol(ctx, c2, T.grid2, T.maxr2, s2); if (r) return r;
+                CK(cudaEventRecord(ctx->ev_tw[1], s2)); CK(cudaStreamWaitEvent(sc, ctx->ev_tw[1], 0));
+                tw_merge_kernel<<<grid_for((int64_t)T.nM * T.nM, 256), 256, 0, sc>>>(T.nM, T.rT, n, ld, S, S2, bp, bs, ctx->d_y.as<double>(), ctx->d_y2.as<double>(),
+                                                                                  ctx->d_SM.as<double>(), T.ldM, ctx->d_rhsM.as<double>());
+                CholArgs cM; cM.S = ctx->d_SM.as<double>(); cM.n = T.nM; cM.ld = T.ldM; cM.lambda = lambda; cM.bp = ctx->d_rhsM.as<double>(); cM.bs = ctx->d_zeroM.as<double>();
+                cM.col_end = ctx->d_colendM.as<int>(); cM.y = ctx->d_yM.as<double>(); cM.dinv = ctx->d_dinv.as<double>(); cM.x = ctx->d_xM.as<double>(); cM.fail = ctx->d_fail.as<int>(); cM.prof = nullptr;
+                r = launch_chol(ctx, cM, T.gridM, T.maxrM, sc); if (r) return r;
+                tw_scatter_kernel<<<grid_for(T.nM, 128), 128, 0, sc>>>(T.nM, T.rT, n, ctx->d_xM.as<double>(), ctx->d_y.as<double>(), ctx->d_y2.as<double>(), ctx->d_xp.as<double>());
+                CK(cudaEventRecord(ctx->ev_tw[2], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[2], 0));
+                CholArgs b1 = c1; b1.p_stop = 0; b1.back_from = T.k; b1.row_done = nullptr;
+                CholArgs b2 = c2; b2.p_stop = 0; b2.back_from = T.k; b2.row_done = nullptr;
+                r = launch_chol(ctx, b1, 1, T.maxr1, sc); if (r) return r;
+                r = launch_chol(ctx, b2, 1, T.maxr2, s2); if (r) return r;
+                CK(cudaEventRecord(ctx->ev_tw[3], s2)); CK(cudaStreamWaitEvent(sc, ctx->ev_tw[3], 0));
+                ctx->tm.total_launches += 7;
+                return BAGPU_OK;
+            };
+            const int chol_sms = ctx->tw.on ? ctx->tw.grid1 + ctx->tw.grid2 : ctx->chol_grid;
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && !getenv("BAGPU_NO_TILES");
@@ -861,14 +1005,12 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     // the Cholesky cluster is queued BEFORE stage_kernel: it takes its SMs now or as soon as the stage drains, in either
                     // case ahead of pair_kernel; stage and pair leave those SMs alone (persistent grids sized for the rest)
                     if (overlap) {
-                        ca.row_done = ctx->d_rowdone.as<unsigned>(); ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1;
                         CK(cudaEventRecord(ctx->ev_fork, st));
                         CK(cudaStreamWaitEvent(ctx->stream_chol, ctx->ev_fork, 0));
-                        { ScopedEv evc(ctx, EV_LINSOLVE, ctx->stream_chol); int rcc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, ctx->stream_chol); if (rcc) return rcc; }
+                        { ScopedEv evc(ctx, EV_LINSOLVE, ctx->stream_chol); int rcc = enqueue_solver(ctx->stream_chol, true); if (rcc) return rcc; }
                         CK(cudaEventRecord(ctx->ev_join, ctx->stream_chol));
-                        ctx->tm.total_launches++;
                     }
-                    const int sm_avail = overlap ? std::max(1, ctx->n_sm - ctx->chol_grid) : ctx->n_sm;
+                    const int sm_avail = overlap ? std::max(1, ctx->n_sm - chol_sms) : ctx->n_sm;
                     const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
                     SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
@@ -883,6 +1025,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         PairArgs PA; PA.row_done = overlap ? ctx->d_rowdone.as<unsigned>() : nullptr;
                         PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1; PA.hpp_diag = nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                         PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
+                        PA.S2 = ctx->tw.on ? S2 : nullptr; PA.n_tot = n; PA.n1 = ctx->tw.n1;
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
                         pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
                         ctx->tm.total_launches++;
@@ -910,11 +1053,10 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             }
             ctx->tm.total_launches++;
             ctx->tm.edge_linearisations += n_active;
-            int rc = all_reduce_sum(ctx, S, ctx->s_elems + 2 * (size_t)std::max(1, n)); if (rc) return rc;
+            int rc = all_reduce_sum(ctx, S, sys_count); if (rc) return rc;
             if (overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             else if (n > 0) {
-                { ScopedEv ev(ctx, EV_LINSOLVE); rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr); if (rc) return rc; }
-                ctx->tm.total_launches++;
+                { ScopedEv ev(ctx, EV_LINSOLVE); rc = enqueue_solver(st, false); if (rc) return rc; }
             }
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
@@ -954,6 +1096,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             rc = read_status(ctx, h, 6); if (rc) return rc;
             int failflag; memcpy(&failflag, &h[5], sizeof(int));
             const bool ok2 = (failflag == 0);
+            if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] trial it=%d q=%d lambda=%.6e chi2 %.9e -> %.9e scale %.3e fail=%d%s\n", it, qmax, lambda, h[0], h[1], h[2] + h[4], failflag, failflag >= 2 ? " (WATCHDOG: the Cholesky waited 2 s for pair_kernel)" : "");
             if (first) { currentChi = h[0]; iniChi = currentChi; first = false; }
             double tempChi = ok2 ? h[1] : DBL_MAX;
             rho = currentChi - tempChi;

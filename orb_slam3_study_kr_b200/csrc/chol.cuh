@@ -43,6 +43,13 @@ struct CholArgs {
     // rows it covers has been accumulated. row_done[a] counts finished items of row a, item_off[a * bw1] is the first item
     // of row a in the plan. nullptr: the system is complete at launch.
     const unsigned *row_done = nullptr; const unsigned *item_off = nullptr; int bw1 = 0;
+    const int *row_pos = nullptr;   // position of camera row a in the item order (items of row a: item_off[row_pos[a] * bw1 ...])
+    // Two-way factorisation (chol_band_kernel): the band is factored from both ends by two clusters that stop at a common
+    // separator block M. p_stop > 0: factor panels [0, p_stop) only, write the partially reduced block columns >= p_stop
+    // back (without lambda) and return; mirror_n > 0: this system is the mirror image (index j <-> mirror_n - 1 - j of the
+    // original ordering: right-hand side, x, camera rows to wait for); back_from > 0: backward substitution only, for panels
+    // back_from - 1 .. 0, with x of the rows >= 32 back_from already in y.
+    int p_stop = 0, mirror_n = 0, back_from = 0, wait_band = 0;
 };
 
 // One warp factors the 32x32 SPD block in shared memory (Ld[r][c], lower part), 8 columns at a time:
@@ -516,10 +523,14 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
     auto load_block = [&](int c) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
         if (a.row_done) {                                  // wait for the camera rows of this block column (pair_kernel)
-            const int a0 = p0 / 6, a1 = (p0 + nb - 1) / 6;
-            if (tid <= a1 - a0) {
-                const int cam = a0 + tid;
-                const unsigned need = a.item_off[(size_t)(cam + 1) * a.bw1] - a.item_off[(size_t)cam * a.bw1];
+            int a0 = p0 / 6, a1 = (p0 + nb - 1) / 6;
+            if (a.mirror_n) {                                  // mirrored system: original columns C_lo..C_hi, rows from C_lo - band up
+                const int c_hi = a.mirror_n - 1 - p0, c_lo = a.mirror_n - 1 - (p0 + nb - 1);
+                a0 = max(0, c_lo - a.wait_band) / 6; a1 = c_hi / 6;
+            }
+            for (int cam = a0 + tid; cam <= a1; cam += CB_THREADS) {
+                const int pos = a.row_pos ? a.row_pos[cam] : cam;
+                const unsigned need = a.item_off[(size_t)(pos + 1) * a.bw1] - a.item_off[(size_t)pos * a.bw1];
                 // pair_kernel runs beside this kernel; if it cannot (a profiler serialising kernels, a starved device) give up after
                 // 2 s and report a failed solve instead of hanging: the LM loop treats it as a rejected trial
                 unsigned long long t_start = 0, t_now = 0;
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
                 while (ld_acquire_gpu(a.row_done + cam) < need) {
                     __nanosleep(100);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-                    if (t_now - t_start > 2000000000ull) { atomicExch(a.fail, 1); break; }
+                    if (t_now - t_start > 2000000000ull) { atomicExch(a.fail, 2 + (a.mirror_n ? 1 : 0)); break; }
                 }
             }
             __syncthreads();
@@ -574,15 +585,18 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
     };
 
     __syncthreads();                                           // s_rend, tri
+    const int Pend = a.p_stop > 0 ? min(a.p_stop, P) : P;      // panels to factor
+    auto ridx = [&](int j) { return a.mirror_n ? a.mirror_n - 1 - j : j; };   // index into bp / bs / x (original ordering)
+    if (a.back_from == 0) {
     int cur = o;
     if (cur < P) load_block(cur);
     cl.sync();
-    if (o == 0 && tid < CB_PG) factor_diag(0, false);
+    if (o == 0 && tid < CB_PG && Pend > 0) factor_diag(0, false);
     __syncthreads();
 
     if (a.prof) t0 = clock64();
     bool failed = false;
-    for (int c = 0; c < P; c++) {
+    for (int c = 0; c < Pend; c++) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
         const int rend = rend_of(c);
         const int R = rend - p0 + 1;
@@ -592,7 +606,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
             if (warp == CB_WARPS - 1) {
                 // forward substitution rides along: y_p = L11^{-1} y_p
                 const double di = invd[lane];
-                double v = (lane < nb) ? (__ldcg(a.bp + p0 + lane) + __ldcg(a.bs + p0 + lane) + __ldcg(a.y + p0 + lane)) * di : 0.0;
+                double v = (lane < nb) ? (__ldcg(a.bp + ridx(p0 + lane)) + __ldcg(a.bs + ridx(p0 + lane)) + __ldcg(a.y + p0 + lane)) * di : 0.0;
 #pragma unroll
                 for (int k = 0; k < CH_NB - 1; k++) {
                     const double yk = __shfl_sync(0xffffffffu, v, k);
@@ -685,7 +699,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
                     __syncwarp();
                 }
                 BT(4);
-                factor_diag(c + 1, R > CH_NB);
+                if (c + 1 < Pend) factor_diag(c + 1, R > CH_NB);   // the separator's diagonal block is not factored here
                 BT(7);
                 cluster_wait();
                 BT(8);
@@ -732,7 +746,32 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         if (o == 0 && tid == 0) { *a.fail = 1; if (a.prof) a.prof[23] = s_fail; }
         return;
     }
+    if (a.p_stop > 0) {
+        // two-way: the block columns of the separator that were loaded (and reduced by the panels factored here) go back to
+        // the band buffer WITHOUT lambda; the merge kernel adds the two partial Schur complements
+        if (cur < P) {
+            const int p0 = cur * CH_NB, nb = min(CH_NB, n - p0);
+            const int R = rend_of(cur) - p0 + 1;
+            if (cur == Pend && Pend > 0 && rend_of(Pend - 1) >= p0) {
+                // the diagonal block still lacks the update of the last panel (its rows were pushed into Lt)
+                for (int e = tid; e < CH_NB * (CH_NB + 1) / 2; e += CB_THREADS) {
+                    const int rc = tri[e], i = rc >> 8, j = rc & 255;
+                    double s0 = 0.0;
+                    for (int k = 0; k < CH_NB; k++) s0 += Lt[i * CB_LD + k] * Lt[j * CB_LD + k];
+                    Cb[i * CB_LD + j] -= s0;
+                }
+                __syncthreads();
+            }
+            for (int j = warp; j < nb; j += CB_WARPS) {
+                double *col = S + (size_t)(p0 + j) * ld + p0;
+                for (int i = j + lane; i < R; i += 32) __stcg(col + i, Cb[i * CB_LD + j] - ((i == j) ? a.lambda : 0.0));
+            }
+        }
+        return;
+    }
     if (o != 0) return;
+    }   // a.back_from == 0
+    else if (o != 0) return;
     BT(15);
     // ---- backward substitution L^T x = y (CTA 0); the band buffer holds 1 / L(j,j) on the diagonal
     const int bs = (maxr + 1) | 1;                             // odd column stride of a prefetched panel
@@ -741,6 +780,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
     double *yv = ysm ? cb_sm : a.y;
     double *pb = cb_sm + n;
     __syncthreads();
+    const int cstart = a.back_from > 0 ? min(a.back_from, P) - 1 : P - 1;
     if (ysm) for (int j = tid; j < n; j += CB_THREADS) yv[j] = __ldcg(a.y + j);
     double *part = yc;
     auto prefetch = [&](int c, double *dst) {                  // columns of panel c, rows p0 .. rend -> dst[j * bs + i]
@@ -752,18 +792,18 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (pref) prefetch(P - 1, pb);
-    for (int c = P - 1; c >= 0; c--) {
+    if (pref && cstart >= 0) prefetch(cstart, pb);
+    for (int c = cstart; c >= 0; c--) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
         const int rbase = p0 + nb;
         const int rend = rend_of(c);
-        double *cbuf = pb + ((P - 1 - c) & 1) * (CH_NB * bs);
+        double *cbuf = pb + ((cstart - c) & 1) * (CH_NB * bs);
         double dv = 1.0;
         if (!pref && warp == 0 && lane < nb) dv = __ldcg(S + (size_t)(p0 + lane) * ld + p0 + lane);
         __syncthreads();                                       // previous panel's x is in yv; its buffer is free
         if (a.prof) { t1 = clock64(); pc[16] += t1 - t0; t0 = t1; }
         if (pref) {
-            if (c > 0) { prefetch(c - 1, pb + ((P - c) & 1) * (CH_NB * bs)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            if (c > 0) { prefetch(c - 1, pb + ((cstart + 1 - c) & 1) * (CH_NB * bs)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
         } else if (warp == CB_WARPS - 1) {
@@ -810,6 +850,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         if (a.prof) { t1 = clock64(); pc[19] += t1 - t0; t0 = t1; }
     }
     __syncthreads();
-    for (int j = tid; j < n; j += CB_THREADS) a.x[j] = yv[j];
+    {   // two-way: only the rows solved here are written (the separator's x is already in place), at their original index
+        const int nx = a.back_from > 0 ? min(n, CH_NB * a.back_from) : n;
+        for (int j = tid; j < nx; j += CB_THREADS) a.x[ridx(j)] = yv[j];
+    }
     if (a.prof && tid == 0) for (int i = 0; i < 24; i++) a.prof[i] = pc[i];
 }

@@ -42,9 +42,10 @@ BA_DEV void stg256(double *p, double a, double b, double c, double d) {
 // ---------------------------------------------------------------------------------------------------------------------
 // plan (upload): observations are sorted landmark-major / pose-ascending, free-pose indices are monotone in the pose index,
 // so inside a landmark e <= e2 implies hidx(e) <= hidx(e2): every pair lands in the upper triangle.
-// Block id = a * bw1 + (b - a) with bw1 = band_blocks + 1 (the envelope agreed at upload bounds b - a).
+// Block id = row_pos[a] * bw1 + (b - a) with bw1 = band_blocks + 1 (the envelope agreed at upload bounds b - a); row_pos is the
+// order in which pair_kernel takes the camera rows (identity, or from both ends when the factorisation is two-way).
 __global__ void pair_count_kernel(int64_t n_obs, const int *__restrict__ lm_ptr, const int *__restrict__ o_pose,
-                                  const int *__restrict__ o_point, const int *__restrict__ hidx, int bw1,
+                                  const int *__restrict__ o_point, const int *__restrict__ hidx, const int *__restrict__ row_pos, int bw1,
                                   unsigned *__restrict__ npairs, unsigned *blk_cnt) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_obs) return;
@@ -56,25 +57,26 @@ __global__ void pair_count_kernel(int64_t n_obs, const int *__restrict__ lm_ptr,
             const int hb = hidx[o_pose[e2]];
             if (hb < 0) continue;
             cnt++;
-            atomicAdd(blk_cnt + (size_t)ha * bw1 + (hb - ha), 1u);
+            atomicAdd(blk_cnt + (size_t)row_pos[ha] * bw1 + (hb - ha), 1u);
         }
     }
     npairs[e] = cnt;
 }
 
 __global__ void pair_gen_kernel(int64_t n_obs, const int *__restrict__ lm_ptr, const int *__restrict__ o_pose,
-                                const int *__restrict__ o_point, const int *__restrict__ hidx, int bw1,
+                                const int *__restrict__ o_point, const int *__restrict__ hidx, const int *__restrict__ row_pos, int bw1,
                                 const unsigned *__restrict__ pair_off, unsigned *__restrict__ keys, int2 *__restrict__ vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_obs) return;
     const int ha = hidx[o_pose[e]];
     if (ha < 0) return;
     const int end = lm_ptr[o_point[e] + 1];
+    const int pa = row_pos[ha];
     unsigned pos = pair_off[e];
     for (int e2 = (int)e; e2 < end; e2++) {
         const int hb = hidx[o_pose[e2]];
         if (hb < 0) continue;
-        keys[pos] = (unsigned)ha * (unsigned)bw1 + (unsigned)(hb - ha);
+        keys[pos] = (unsigned)pa * (unsigned)bw1 + (unsigned)(hb - ha);
         vals[pos] = make_int2((int)e, e2);
         pos++;
     }
@@ -85,13 +87,13 @@ __global__ void pair_item_count_kernel(int nblk, const unsigned *__restrict__ bl
     if (i < nblk) item_cnt[i] = (blk_cnt[i] + PK_CHUNK - 1) / PK_CHUNK;
 }
 
-__global__ void pair_item_fill_kernel(int nblk, int bw1, const unsigned *__restrict__ blk_off, const unsigned *__restrict__ blk_cnt,
+__global__ void pair_item_fill_kernel(int nblk, int bw1, const int *__restrict__ row_of_pos, const unsigned *__restrict__ blk_off, const unsigned *__restrict__ blk_cnt,
                                       const unsigned *__restrict__ item_off, PairItem *__restrict__ items) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk) return;
     const unsigned cnt = blk_cnt[i];
     if (!cnt) return;
-    const int a = i / bw1, b = a + (i - a * bw1);
+    const int pa = i / bw1, a = row_of_pos[pa], b = a + (i - pa * bw1);
     const unsigned off = blk_off[i];
     unsigned io = item_off[i];
     for (unsigned c = 0; c < cnt; c += PK_CHUNK) {
@@ -301,6 +303,7 @@ struct PairArgs {
     double *part;                 // [n_items][PK_PART] partial sums of blocks cut into several items
     unsigned *blk_done; int bw1;  // finished items per block (never reset: the last finisher is the one that completes a multiple of nit)
     unsigned *row_done;           // optional: finished items per camera row (chol_band_kernel runs beside this kernel)
+    double *S2; int n_tot, n1;    // optional (two-way factorisation): elements with column >= n1 go to the mirrored system S2
     double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit (only the Dr sums of the diagonal blocks)
 };
 
@@ -401,14 +404,18 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
             continue;
         }
         // ---- the block's total: at most two adds per element of S onto the zeroed system (exact in any order)
-        double *Sblk = P.S + (size_t)(6 * I.a) * P.ld + 6 * I.b;
+        auto elem = [&](int r, int c) -> double * {                                  // element (r, c) of block (a, b), r <= c on the diagonal block
+            const int R = 6 * I.a + r, C = 6 * I.b + c;
+            if (P.S2 && C >= P.n1) return P.S2 + (size_t)(P.n_tot - 1 - C) * P.ld + (P.n_tot - 1 - R);
+            return P.S + (size_t)R * P.ld + C;
+        };
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int o = lane + 32 * h;
             const double s = h ? sz1 : sz0;
             if (o < 36) {
                 const int r = o / 6, c = o - 6 * r;
-                if ((!diag || c >= r) && s != 0.0) atomicAdd(Sblk + (size_t)r * P.ld + c, -s);
+                if ((!diag || c >= r) && s != 0.0) atomicAdd(elem(r, c), -s);
             }
         }
         if (diag) {
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
                     if (o < 21) {
                         int r = 0, t = o;
                         while (t >= 6 - r) { t -= 6 - r; r++; }
-                        atomicAdd(Sblk + (size_t)r * P.ld + r + t, s);
+                        atomicAdd(elem(r, r + t), s);
                     } else if (o < 27) atomicAdd(P.bp + 6 * I.a + (o - 21), s);
                     else atomicAdd(P.bs + 6 * I.a + (o - 27), s);
                 }
