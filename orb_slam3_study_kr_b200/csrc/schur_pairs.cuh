@@ -24,6 +24,9 @@
 #ifndef PK_CHUNK
 #define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
 #endif
+#ifndef PK_MINB
+#define PK_MINB 3
+#endif
 #define PK_THREADS 128
 #define PK_WARPS (PK_THREADS / 32)
 #define PK_RED_LD 33
@@ -322,7 +325,7 @@ BA_DEV void pair_accumulate(const double *__restrict__ Z, int ex, int ey, double
             acc[6 * r + c] += x[3 * r] * y[3 * c] + x[3 * r + 1] * y[3 * c + 1] + x[3 * r + 2] * y[3 * c + 2];
 }
 
-__global__ void __launch_bounds__(PK_THREADS, 3) pair_kernel(PairArgs P) {
+__global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
     extern __shared__ double pk_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *red = pk_sm + warp * 36 * PK_RED_LD;
