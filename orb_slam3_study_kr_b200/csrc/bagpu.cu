@@ -831,7 +831,9 @@ size_t chol_band_smem(int n, int maxr) {
     const size_t need = chol_band_smem_min(maxr);
     const size_t bs = (size_t)((maxr + 1) | 1);
     const size_t back = sizeof(double) * ((size_t)n + 2 * CH_NB * bs);
+    const size_t back3 = sizeof(double) * ((size_t)n + 3 * CH_NB * bs);      // pipelined backward substitution: three panel buffers
     const size_t ysm = sizeof(double) * (size_t)n;
+    if (back3 <= cap && !getenv("BAGPU_NO_BACK3")) return std::max(need, back3);
     if (back <= cap) return std::max(need, back);
     if (ysm <= cap) return std::max(need, ysm);
     return need;

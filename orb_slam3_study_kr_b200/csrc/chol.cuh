@@ -792,6 +792,77 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const bool pref3 = cstart >= 0 && n + 3 * CH_NB * bs <= dyn_doubles;   // three panel buffers: software-pipelined variant
+    if (pref3) {
+        // While warp 0 runs the triangular chain of panel c, warps 1..15 form the dot products of panel c-1 with everything
+        // that is already known (the rows from its second block down) and prefetch panel c-2; the chain of panel c-1 then only
+        // adds the 32 rows panel c has just produced. One barrier per panel.
+        __shared__ double partA[2][CH_NB];
+        auto bufof = [&](int c) { return pb + (c % 3) * (CH_NB * bs); };
+        auto prefetch_w = [&](int c) {
+            const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
+            const int R = rend_of(c) - p0 + 1;
+            double *dst = bufof(c);
+            for (int j = warp - 1; j < nb; j += CB_WARPS - 1) {
+                const double *col = S + (size_t)(p0 + j) * ld + p0;
+                for (int i = j + lane; i < R; i += 32) cp_async8(dst + j * bs + i, col + i);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto old_dots = [&](int c) {
+            const int p0 = c * CH_NB, nb = min(CH_NB, n - p0), rbase = p0 + nb, rend = rend_of(c);
+            const double *cb = bufof(c);
+            for (int j = warp - 1; j < CH_NB; j += CB_WARPS - 1) {
+                double sacc = 0.0;
+                if (j < nb) {
+                    const double *col = cb + j * bs - p0;
+#pragma unroll 4
+                    for (int i = rbase + CH_NB + lane; i <= rend; i += 32) sacc += col[i] * yv[i];
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+                if (lane == 0) partA[c & 1][j] = sacc;
+            }
+        };
+        if (warp > 0) {
+            prefetch_w(cstart);
+            if (cstart > 0) prefetch_w(cstart - 1);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                       // yv loaded, the first two panels landed
+        if (warp > 0) old_dots(cstart);
+        if (a.prof) { t1 = clock64(); pc[16] += t1 - t0; t0 = t1; }
+        for (int c = cstart; c >= 0; c--) {
+            if (warp > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                   // x of panel c+1 in yv, partA of panel c complete, panel c-1 landed
+            if (warp == 0) {
+                const int p0 = c * CH_NB, nb = min(CH_NB, n - p0), rbase = p0 + nb, rend = rend_of(c);
+                const double *cb = bufof(c);
+                const double dv = (lane < nb) ? cb[lane * bs + lane] : 1.0;
+                const int nnew = max(0, min(CH_NB, rend - rbase + 1));
+                double nd0 = 0.0, nd1 = 0.0;
+                if (lane < nb) {
+                    const double *col = cb + lane * bs + nb;
+                    int i = 0;
+                    for (; i + 1 < nnew; i += 2) { nd0 += col[i] * yv[rbase + i]; nd1 += col[i + 1] * yv[rbase + i + 1]; }
+                    if (i < nnew) nd0 += col[i] * yv[rbase + i];
+                }
+                const double *lp = cb + lane * bs;
+                double v = (lane < nb) ? (yv[p0 + lane] - partA[c & 1][lane] - (nd0 + nd1)) * dv : 0.0;
+#pragma unroll
+                for (int i = CH_NB - 1; i >= 1; i--) {
+                    const double xi = __shfl_sync(0xffffffffu, v, i);
+                    const double l = (lane < i && i < nb) ? lp[i] * dv : 0.0;
+                    v -= l * xi;
+                }
+                if (lane < nb) yv[p0 + lane] = v;
+            } else {
+                if (c >= 2) prefetch_w(c - 2);
+                if (c >= 1) old_dots(c - 1);
+            }
+        }
+        if (a.prof) { t1 = clock64(); pc[19] += t1 - t0; t0 = t1; }
+    } else {
     if (pref && cstart >= 0) prefetch(cstart, pb);
     for (int c = cstart; c >= 0; c--) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
@@ -849,6 +920,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         }
         if (a.prof) { t1 = clock64(); pc[19] += t1 - t0; t0 = t1; }
     }
+    }   // !pref3
     __syncthreads();
     {   // two-way: only the rows solved here are written (the separator's x is already in place), at their original index
         const int nx = a.back_from > 0 ? min(n, CH_NB * a.back_from) : n;
