@@ -578,6 +578,28 @@ __global__ void reduce_partials_kernel(int n, const double *a, const double *b, 
     if (threadIdx.x == 0) { out[0] = sa[0]; out[1] = sb[0] + (add_b ? *add_b : 0.0); out[2] = sc[0]; }
 }
 
+// End of an LM trial: the three sums the host decides on, in one launch (block 0: chi2 at the linearisation point, block 1:
+// chi2 at the trial state, block 2: landmark part of computeScale), each a fixed-order reduction of per-CTA partials
+// (+ the partials of the long-track kernels), and the failure flag next to them.
+struct TrialSums { const double *a[3]; int na[3]; const double *b[3]; int nb[3]; const int *fail; double *out; };
+__global__ void finish_trial_kernel(TrialSums T) {
+    __shared__ double sh[256];
+    const int q = blockIdx.x;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < T.na[q]; i += 256) v += T.a[q][i];
+    if (T.b[q]) for (int i = threadIdx.x; i < T.nb[q]; i += 256) v += T.b[q][i];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        T.out[q] = sh[0];
+        if (q == 0) T.out[5] = (double)*T.fail;
+    }
+}
+
 // out[perm[i]] = in[i]  (sorted order -> caller's edge order)
 template <typename T>
 __global__ void scatter_perm_kernel(int64_t n, const int *__restrict__ perm, const T *__restrict__ in, T *out) {

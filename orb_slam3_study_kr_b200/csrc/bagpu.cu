@@ -349,7 +349,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
                              (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel,
                              (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel,
-                             (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel,
+                             (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel, (const void *)finish_trial_kernel,
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
                              (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
                              (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
@@ -1107,19 +1107,21 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             ctx->tm.total_launches += 2;
             ctx->tm.edge_linearisations += 0; ctx->tm.edge_evaluations += n_active;
             // dstat[0] = chi2 at the linearisation point, [1] = trial chi2, [2] = landmark part of scale, [4] = pose part of scale
-            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_b, part_chi_b, nullptr, nullptr, nullptr, nullptr, 0, dstat + 12, have_wide_part ? part_chi_w : nullptr, n_part_w);
-            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_chi_u, nullptr, nullptr, nullptr, nullptr, 0, dstat + 16, upd_wide ? part_chi_uw : nullptr, G);
-            reduce_partials_kernel<<<1, 256, 0, st>>>(n_part_u, part_scale, nullptr, nullptr, nullptr, nullptr, 0, dstat + 8, upd_wide ? part_scale_w : nullptr, G);
-            ctx->tm.total_launches += 3;
-            CK(cudaMemcpyAsync(dstat, dstat + 12, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(dstat + 1, dstat + 16, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(dstat + 2, dstat + 8, sizeof(double), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(dstat + 5, ctx->d_fail.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            {
+                TrialSums TS;
+                TS.a[0] = part_chi_b; TS.na[0] = n_part_b; TS.b[0] = have_wide_part ? part_chi_w : nullptr; TS.nb[0] = n_part_w;
+                TS.a[1] = part_chi_u; TS.na[1] = n_part_u; TS.b[1] = upd_wide ? part_chi_uw : nullptr; TS.nb[1] = G;
+                TS.a[2] = part_scale; TS.na[2] = n_part_u; TS.b[2] = upd_wide ? part_scale_w : nullptr; TS.nb[2] = G;
+                TS.fail = ctx->d_fail.as<int>(); TS.out = dstat;
+                finish_trial_kernel<<<3, 256, 0, st>>>(TS);
+                ctx->tm.total_launches++;
+            }
             rc = all_reduce_sum(ctx, dstat, 3); if (rc) return rc;
+            rc = all_reduce_max(ctx, dstat + 5, 1); if (rc) return rc;       // a landmark factor can fail on one rank only
             CK(cudaGetLastError());
             double h[6];
             rc = read_status(ctx, h, 6); if (rc) return rc;
-            int failflag; memcpy(&failflag, &h[5], sizeof(int));
+            const int failflag = (int)h[5];
             const bool ok2 = (failflag == 0);
             if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] trial it=%d q=%d lambda=%.6e chi2 %.9e -> %.9e scale %.3e fail=%d%s\n", it, qmax, lambda, h[0], h[1], h[2] + h[4], failflag, failflag >= 2 ? " (WATCHDOG: the Cholesky waited 2 s for pair_kernel)" : "");
             if (first) { currentChi = h[0]; iniChi = currentChi; first = false; }
