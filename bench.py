@@ -39,6 +39,11 @@ METRIC = "global BA edge passes/s (LM linearisations + evaluations per second; L
 N_ITER = 20
 
 
+def workload_name(n_obs: int) -> str:
+    return ("C4 global BA, weak-scaled: 500 KFs (1 fixed) common, 200k landmarks / %d observations per GPU, "
+            "seed 4, EuRoC stereo+mono, non-robust, optimize(%d)" % (n_obs, N_ITER))
+
+
 # ----------------------------------------------------------------------------- distributed helpers (also used by tests)
 def _dist():
     import torch.distributed as dist
@@ -177,8 +182,8 @@ def run_reference(args, rank: int, world: int):
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "lm_iters_per_s": iters / tot_s,
-            "config": {"workload": "C4 global BA: 500 KFs (1 fixed), 200k landmarks, %d observations, seed 4, non-robust" % p.n_obs,
-                       "sample": "%d of %d LM iterations per step" % (args.ref_iters, N_ITER)},
+            "config": {"workload": workload_name(p.n_obs),
+                       "sample": "%d of %d LM iterations per step, rank 0's shard (the rate does not depend on N)" % (args.ref_iters, N_ITER)},
             "cpu_baseline": {"value": v, "unit": "edge passes/s", "cores": 1, "kind": "port",
                              "sample": "%d steps x %d LM iterations of the C4 map, oracle/ba_ref.cpp -O3 -march=x86-64-v3, 1 thread "
                                        "(reference g2o is built without OpenMP)" % (args.steps, args.ref_iters)},
@@ -306,8 +311,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         line = {"metric": METRIC, "value": value, "unit": "edge passes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C4 global BA, weak-scaled: 500 KFs (1 fixed) common, 200k landmarks / %d observations per GPU, "
-                                       "seed 4, EuRoC stereo+mono, non-robust, optimize(%d)" % (p.n_obs, N_ITER),
+                "config": {"workload": workload_name(p.n_obs),
                            "sharding": "landmarks per rank, NCCL all-reduce of the reduced camera system per LM trial" if world > 1 else "1 GPU",
                            "l2": "flushed between steps (256 MiB write)", "timing": "CUDA events on the library stream, max over ranks"},
                 "lm_iters_per_s": iters_per_s, "lm_iterations_per_step": acc["lm_iterations"] / args.steps,
