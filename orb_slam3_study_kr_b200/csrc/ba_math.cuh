@@ -234,7 +234,8 @@ BA_DEV double edge_residual(int kind, const Cam &c, const Pose &T, const Pose *T
 // types_six_dof_expmap.cpp:228-274,375-404 (same entries, different association of the products).
 struct EdgeLin {
     double A[9];      // rows 0..dim-1 used
-    double B[18];
+    double B[18];     // B = M [ -[X_l]x | I ]: columns 3..5 are M = Jn R_rl
+    double xl[3];     // the point in the (left) camera frame
 };
 
 BA_DEV void edge_linearize(int kind, const Cam &c, const Pose &T, const Pose *Trl, double X, double Y, double Z, EdgeLin &L) {
@@ -272,6 +273,7 @@ BA_DEV void edge_linearize(int kind, const Cam &c, const Pose &T, const Pose *Tr
 #pragma unroll
         for (int i = 0; i < 9; i++) M[i] = Jn[i];
     }
+    L.xl[0] = xl; L.xl[1] = yl; L.xl[2] = zl;
 #pragma unroll
     for (int r = 0; r < 3; r++) {
 #pragma unroll

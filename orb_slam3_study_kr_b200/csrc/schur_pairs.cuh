@@ -7,7 +7,7 @@
 //   stage_kernel / stage_wide_kernel   landmark-major (lane = observation). Linearise, reduce the landmark's Hll / bl,
 //       factor Hll + lambda I = L L^T (3x3 Cholesky, in registers) and write per observation
 //         Z  = W L^-T                      (6x3; W = rho1 w B^T A is the Hpl block)   -> Z Z'^T = W (Hll+lambda I)^-1 W'^T
-//         Dr = [ w B^T B (21) | B^T g (6) | -Z L^-1 bl (6) ]                          -> the per-camera sums
+//         Dr = [ w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 bl (6) ], B = M [-[X_l]x | I]    -> the per-camera sums (Hpp, bp, bs)
 //   pair_kernel    camera-pair-major. At upload the device lists, for every upper block (a, b) of the reduced system,
 //       the observation pairs (e_a, e_b) of the landmarks both cameras see, sorted by block (pair_plan_*). A warp takes
 //       one chunk of one block's list, each lane accumulates Z_a Z_b^T of its entries in 36 registers, the warp sums the
@@ -20,7 +20,7 @@
 #include "ba_kernels.cuh"
 
 #define ZR_STRIDE 20                       // 18 used: 160-byte records = five 32-byte sectors, one 256-bit access each
-#define DR_STRIDE 36                       // 33 used: nine sectors
+#define DR_STRIDE 20                       // 18 used: [w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 b_l (6)], five sectors
 #ifndef PK_CHUNK
 #define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
 #endif
@@ -166,17 +166,25 @@ BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *_
     z[18] = z[19] = 0.0;
 #pragma unroll
     for (int i = 0; i < ZR_STRIDE / 4; i++) stg256(zo + 4 * i, z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+    // B = M [ -[X_l]x | I ] (M = columns 3..5 of B), so w B^T B and B^T g follow from N = w M^T M (6), X_l (3) and M^T g (3):
+    // pair_kernel rebuilds the 27 values when it sums the records of a camera
     double d[DR_STRIDE];
-    int p = 0;
+    {
+        const double m00 = B[3], m01 = B[4], m02 = B[5], m10 = B[9], m11 = B[10], m12 = B[11], m20 = B[15], m21 = B[16], m22 = B[17];
+        d[0] = act ? E.wgt * (m00 * m00 + m10 * m10 + m20 * m20) : 0.0;
+        d[1] = act ? E.wgt * (m00 * m01 + m10 * m11 + m20 * m21) : 0.0;
+        d[2] = act ? E.wgt * (m00 * m02 + m10 * m12 + m20 * m22) : 0.0;
+        d[3] = act ? E.wgt * (m01 * m01 + m11 * m11 + m21 * m21) : 0.0;
+        d[4] = act ? E.wgt * (m01 * m02 + m11 * m12 + m21 * m22) : 0.0;
+        d[5] = act ? E.wgt * (m02 * m02 + m12 * m12 + m22 * m22) : 0.0;
+        d[6] = act ? E.L.xl[0] : 0.0; d[7] = act ? E.L.xl[1] : 0.0; d[8] = act ? E.L.xl[2] : 0.0;
+        d[9] = act ? (m00 * E.g0 + m10 * E.g1 + m20 * E.g2) : 0.0;
+        d[10] = act ? (m01 * E.g0 + m11 * E.g1 + m21 * E.g2) : 0.0;
+        d[11] = act ? (m02 * E.g0 + m12 * E.g1 + m22 * E.g2) : 0.0;
+    }
 #pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int c = a; c < 6; c++) { d[p] = act ? E.wgt * (B[a] * B[c] + B[6 + a] * B[6 + c] + B[12 + a] * B[12 + c]) : 0.0; p++; }
-#pragma unroll
-    for (int a = 0; a < 6; a++) d[21 + a] = act ? (B[a] * E.g0 + B[6 + a] * E.g1 + B[12 + a] * E.g2) : 0.0;
-#pragma unroll
-    for (int a = 0; a < 6; a++) d[27 + a] = bs[a];
-    d[33] = d[34] = d[35] = 0.0;
+    for (int a = 0; a < 6; a++) d[12 + a] = bs[a];
+    d[18] = d[19] = 0.0;
 #pragma unroll
     for (int i = 0; i < DR_STRIDE / 4; i++) stg256(dout + 4 * i, d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
 }
@@ -357,15 +365,32 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
         }
         if (diag) {
             // Hpp, bp, bs of camera a: sum of the Dr records of its observations (the (e, e) entries)
-            double d[DR_STRIDE];
+            double d[33];
 #pragma unroll
-            for (int i = 0; i < DR_STRIDE; i++) d[i] = 0.0;
+            for (int i = 0; i < 33; i++) d[i] = 0.0;
             for (int i = I.begin + lane; i < I.end; i += 32) {
                 const int2 en = __ldg(P.entries + i);
                 if (en.x != en.y) continue;
                 const double *pd = P.Dr + DR_STRIDE * (size_t)en.x;
+                double v[DR_STRIDE];
 #pragma unroll
-                for (int q = 0; q < DR_STRIDE / 4; q++) { double v[4]; ldg256(pd + 4 * q, v); d[4 * q] += v[0]; d[4 * q + 1] += v[1]; d[4 * q + 2] += v[2]; d[4 * q + 3] += v[3]; }
+                for (int q = 0; q < DR_STRIDE / 4; q++) ldg256(pd + 4 * q, v + 4 * q);
+                // w B^T B = [P | I]^T N [P | I] with P = -[X]x; T = N P, TL = P^T T
+                const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = v[6], y = v[7], z = v[8];
+                const double t00 = -z * n01 + y * n02, t01 = z * n00 - x * n02, t02 = -y * n00 + x * n01;
+                const double t10 = -z * n11 + y * n12, t11 = z * n01 - x * n12, t12 = -y * n01 + x * n11;
+                const double t20 = -z * n12 + y * n22, t21 = z * n02 - x * n22, t22 = -y * n02 + x * n12;
+                d[0] += -z * t10 + y * t20; d[1] += -z * t11 + y * t21; d[2] += -z * t12 + y * t22;      // TL row 0
+                d[3] += t00; d[4] += t10; d[5] += t20;                                                    // H(0, 3..5) = T(.,0)
+                d[6] += z * t01 - x * t21; d[7] += z * t02 - x * t22;                                     // TL(1,1), TL(1,2)
+                d[8] += t01; d[9] += t11; d[10] += t21;
+                d[11] += -y * t02 + x * t12;                                                              // TL(2,2)
+                d[12] += t02; d[13] += t12; d[14] += t22;
+                d[15] += n00; d[16] += n01; d[17] += n02; d[18] += n11; d[19] += n12; d[20] += n22;
+                d[21] += -z * v[10] + y * v[11]; d[22] += z * v[9] - x * v[11]; d[23] += -y * v[9] + x * v[10];   // B^T g = [P^T m; m]
+                d[24] += v[9]; d[25] += v[10]; d[26] += v[11];
+#pragma unroll
+                for (int q = 0; q < 6; q++) d[27 + q] += v[12 + q];
             }
 #pragma unroll
             for (int i = 0; i < 33; i++) red[i * PK_RED_LD + lane] = d[i];
