@@ -132,8 +132,8 @@ struct bagpu_ctx {
     DevBuf d_pose_a, d_pose_b, d_pose_init, d_pt_a, d_pt_b, d_pt_init, d_meta_init;
     DevBuf d_sys;                      // [S (n*ld) | bp (n) | bs (n) | S2 (two-way: mirrored lower half) | hpp_diag (n)]; S .. S2 contiguous (one all-reduce)
     DevBuf d_y, d_colend, d_dinv, d_widelist, d_tasks;
-    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone;
-    int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, parts_stride = 1;
+    DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone, d_Lm;
+    int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, updz_grid = 1, parts_stride = 1;
     int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
     size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
@@ -348,7 +348,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         cudaFuncAttributes fa;
         const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
                              (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel,
-                             (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel,
+                             (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel, (const void *)update_z_kernel,
                              (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel, (const void *)finish_trial_kernel,
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
                              (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
@@ -369,7 +369,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
                       &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_Z, &ctx->d_Dr, &ctx->d_entries, &ctx->d_items, &ctx->d_pk_keys, &ctx->d_pk_keys2, &ctx->d_pk_vals,
-                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp, &ctx->d_rowdone, &ctx->d_part, &ctx->d_blkdone,
+                      &ctx->d_npairs, &ctx->d_pairoff, &ctx->d_blkcnt, &ctx->d_blkoff, &ctx->d_itemcnt, &ctx->d_itemoff, &ctx->d_cubtmp, &ctx->d_rowdone, &ctx->d_part, &ctx->d_blkdone, &ctx->d_Lm,
                       &ctx->d_parts, &ctx->d_status, &ctx->d_chi2, &ctx->d_depth, &ctx->d_out_chi2, &ctx->d_out_u8a, &ctx->d_out_u8b,
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
@@ -701,6 +701,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             int occ_u = 0, occ_st = 0, occ_sw = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, update_packed_kernel, ST_THREADS, 0));
             ctx->upd_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_u), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
+            int occ_z = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_z, update_z_kernel, ST_THREADS, 0));
+            ctx->updz_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_z), (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_st, stage_kernel, ST_THREADS, 0));
             ctx->stage_occ = std::max(1, occ_st);
             ctx->stage_grid = std::max(1, std::min(ctx->n_sm * ctx->stage_occ, (ctx->n_tasks + ST_WARPS - 1) / ST_WARPS));
@@ -762,6 +765,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 CK(cudaGetLastError());
             }
             CK(ctx->d_Z.ensure(sizeof(double) * ZR_STRIDE * ne)); CK(ctx->d_Dr.ensure(sizeof(double) * DR_STRIDE * ne));
+            CK(ctx->d_Lm.ensure(sizeof(double) * LM_STRIDE * (size_t)Np));
             CK(ctx->d_part.ensure(sizeof(double) * PK_PART * (size_t)std::max(1, ctx->n_items)));
             CK(ctx->d_blkdone.ensure(sizeof(unsigned) * ((size_t)nblk + 1)));
             CK(cudaMemsetAsync(ctx->d_blkdone.p, 0, sizeof(unsigned) * ((size_t)nblk + 1), sp));
@@ -784,7 +788,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel, BUILD_THREADS, 0));
     ctx->build_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ), (Np + BUILD_WARPS - 1) / BUILD_WARPS));
-    ctx->parts_stride = std::max(std::max(ctx->build_grid, ctx->stage_grid + ctx->stage_wide_grid), ctx->upd_grid);
+    ctx->parts_stride = std::max(std::max(ctx->build_grid, ctx->stage_grid + ctx->stage_wide_grid), std::max(ctx->upd_grid, ctx->updz_grid));
     CK(ctx->d_parts.ensure(sizeof(double) * 7 * (size_t)ctx->parts_stride));
     CK(ctx->d_status.ensure(sizeof(double) * 32));
     CK(ctx->d_fail.ensure(sizeof(int) * 4));
@@ -941,7 +945,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 // the same stage / pair kernels as the trials (fixed summation order): Dr records, then the diagonal blocks only
                 ScopedEv ev(ctx, EV_BUILD);
                 StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
-                SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = 1.0; SA.part_chi2 = part_chi_b; SA.part_maxdiag = part_max;
+                SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = 1.0; SA.part_chi2 = part_chi_b; SA.part_maxdiag = part_max;
                 SA.fail = ctx->d_fail.as<int>();
                 stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                 n_part0 = ctx->stage_grid;
@@ -1038,7 +1042,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     const int sm_avail = overlap ? std::max(1, ctx->n_sm - chol_sms) : ctx->n_sm;
                     const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
-                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
+                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
                     stage_kernel<<<sgrid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                     n_part_b = sgrid;
                     if (ctx->n_wide > 0) {             // landmarks with more than 32 observations: warp = landmark
@@ -1093,8 +1097,14 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 ScopedEv ev(ctx, EV_UPDATE);
                 if (packed) {
                     UpdateTasks K; K.tasks = ctx->d_tasks.as<int2>(); K.n_tasks = ctx->n_tasks;
-                    update_packed_kernel<<<ctx->upd_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U, K);
-                    n_part_u = ctx->upd_grid;
+                    if (tiled && ctx->n_items > 0 && !getenv("BAGPU_UPDATE_RELIN")) {
+                        // back-substitution from the Z records of this trial's stage (no second linearisation)
+                        update_z_kernel<<<ctx->updz_grid, ST_THREADS, 0, st>>>(D, ctx->pt_cur, U, K, ctx->d_Z.as<double>(), ctx->d_Lm.as<double>());
+                        n_part_u = ctx->updz_grid;
+                    } else {
+                        update_packed_kernel<<<ctx->upd_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, U, K);
+                        n_part_u = ctx->upd_grid;
+                    }
                     if (ctx->n_wide > 0) {
                         UpdateOut UW = U; UW.part_chi2 = part_chi_uw; UW.part_scale = part_scale_w; UW.lm_list = ctx->d_widelist.as<int>(); UW.n_list = ctx->n_wide;
                         update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, UW);

@@ -22,6 +22,7 @@
 #define ZR_STRIDE 20                       // 18 used: 160-byte records = five 32-byte sectors, one 256-bit access each
 #define DR_STRIDE 20                       // 18 used: [w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 b_l (6)], five sectors
 #ifndef PK_CHUNK
+#define LM_STRIDE 12
 #define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
 #endif
 #ifndef PK_MINB
@@ -194,6 +195,7 @@ struct StageArgs {
     int n_tasks;
     const int *lm_list; int n_list;   // stage_wide_kernel: landmarks with more than 32 observations
     double *Z, *Dr;
+    double *Lm;                   // [n_points][LM_STRIDE] landmark records: L^-1 diag / L off-diag (6) | c = L^-1 bl (3) | bl (3)
     double lambda;
     double *part_chi2;            // [gridDim.x]
     double *part_maxdiag;         // optional [gridDim.x]: max |Hll diagonal| (computeLambdaInit)
@@ -242,6 +244,12 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, con
         // level-1 edges on a free pose still own a record (the pair lists do not change between rounds): exact zeros
         const int hx = in ? __ldg(D.pose_hidx + __ldg(D.o_pose + e)) : -1;
         if (hx >= 0) lane_emit(E, F, e, S.Z, S.Dr);
+        if (in && lane == head) {                              // what update_z_kernel needs to back-substitute this landmark
+            double *lm = S.Lm + LM_STRIDE * (size_t)j;
+            stg256(lm, F.i00, F.l10, F.l20, F.i11);
+            stg256(lm + 4, F.l21, F.i22, F.c0, F.c1);
+            stg256(lm + 8, F.c2, r[6], r[7], r[8]);
+        }
     }
     if (bad) atomicOr(S.fail, 1);
     chi_acc = warp_allsum(chi_acc);
@@ -466,5 +474,103 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
             __syncwarp();
             if (lane == 0) atomicAdd(P.row_done + I.a, (unsigned)I.nit);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// update_z_kernel: update_packed_kernel without the second linearisation. With Hll + lambda I = L L^T and Z = W L^-T from the
+// stage, the back-substitution x_l = (Hll + lambda I)^-1 (b_l - W^T x_p) (block_solver.hpp:459-483) is
+// x_l = L^-T (L^-1 b_l - sum_obs Z^T x_p): one 160-byte record and 18 FMA per observation, three sums per landmark. Then the
+// same evaluation of every edge at the trial state as update_packed_kernel (computeActiveErrors + activeRobustChi2) and the
+// landmark part of computeScale.
+__global__ void __launch_bounds__(ST_THREADS, 3) update_z_kernel(BaDev D, const double *__restrict__ pt, UpdateOut O, UpdateTasks K,
+                                                                 const double *__restrict__ Zr, const double *__restrict__ Lm) {
+    __shared__ double s_chi[ST_WARPS], s_sc[ST_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double chi_acc = 0.0, sc_acc = 0.0;
+    for (int t = blockIdx.x * ST_WARPS + warp; t < K.n_tasks; t += gridDim.x * ST_WARPS) {
+        const int2 tk = K.tasks[t];
+        const int e_first = __ldg(D.lm_ptr + tk.x), nobs = __ldg(D.lm_ptr + tk.y) - e_first;
+        const bool in = lane < nobs;
+        const int e = e_first + lane;
+        const int j = in ? __ldg(D.o_point + e) : -1;
+        int head = lane, segl = 1;
+        if (in) {
+            const int p0 = __ldg(D.lm_ptr + j);
+            head = lane - (e - p0); segl = __ldg(D.lm_ptr + j + 1) - p0;
+        }
+        const int seg_last = head + segl - 1;
+        const uint32_t m = in ? D.o_meta[e] : META_LEVEL1;
+        const bool valid = !(m & META_LEVEL1);
+        const int ip = in ? __ldg(D.o_pose + e) : 0;
+        const int hx = valid ? __ldg(D.pose_hidx + ip) : -1;
+        double r[3] = {0.0, 0.0, 0.0};
+        if (hx >= 0) {                                         // Z^T x_p
+            double z[ZR_STRIDE];
+#pragma unroll
+            for (int q = 0; q < ZR_STRIDE / 4; q++) ldg256(Zr + ZR_STRIDE * (size_t)e + 4 * q, z + 4 * q);
+            const double *x = O.xp + 6 * hx;
+#pragma unroll
+            for (int a = 0; a < 6; a++) { const double xa = __ldg(x + a); r[0] += z[3 * a] * xa; r[1] += z[3 * a + 1] * xa; r[2] += z[3 * a + 2] * xa; }
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const bool take = in && lane + off <= seg_last;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double o = __shfl_down_sync(0xffffffffu, r[i], off);
+                if (take) r[i] += o;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) r[i] = __shfl_sync(0xffffffffu, r[i], head);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned segmask = (segl >= 32 ? 0xffffffffu : ((1u << segl) - 1u)) << head;
+        const bool any_act = (vmask & segmask) != 0u;
+        double nx = 0.0, ny = 0.0, nz = 1.0;
+        if (in) {
+            const double X = __ldg(pt + 3 * (size_t)j), Y = __ldg(pt + 3 * (size_t)j + 1), Z = __ldg(pt + 3 * (size_t)j + 2);
+            nx = X; ny = Y; nz = Z;
+            if (any_act) {
+                double f[LM_STRIDE];
+#pragma unroll
+                for (int q = 0; q < LM_STRIDE / 4; q++) ldg256(Lm + LM_STRIDE * (size_t)j + 4 * q, f + 4 * q);
+                // f = i00 l10 l20 i11 | l21 i22 c0 c1 | c2 bl0 bl1 bl2 ;  L^T x = c - Z^T x_p
+                const double u0 = f[6] - r[0], u1 = f[7] - r[1], u2 = f[8] - r[2];
+                const double x2 = u2 * f[5];
+                const double x1 = (u1 - f[4] * x2) * f[3];
+                const double x0 = (u0 - f[1] * x1 - f[2] * x2) * f[0];
+                nx = X + x0; ny = Y + x1; nz = Z + x2;
+                if (lane == head) sc_acc += x0 * (O.lambda * x0 + f[9]) + x1 * (O.lambda * x1 + f[10]) + x2 * (O.lambda * x2 + f[11]);
+            }
+            if (lane == head) { O.pt_trial[3 * (size_t)j] = nx; O.pt_trial[3 * (size_t)j + 1] = ny; O.pt_trial[3 * (size_t)j + 2] = nz; }
+        }
+        // evaluation at the trial state
+        if (in && valid) {
+            const int kind = META_KIND(m);
+            const Cam cam = load_cam(D.cams + META_CAM(m));
+            const Pose T = load_pose(O.pose_trial + 7 * (size_t)ip);
+            Pose Trl;
+            if (kind == BAGPU_EDGE_BODY) Trl = load_pose(D.rigs + 7 * META_RIG(m));
+            const double om = __ldg(D.o_w + e);
+            double r0, r1, r2;
+            edge_residual(kind, cam, T, &Trl, nx, ny, nz, __ldg(D.o_u + e), __ldg(D.o_v + e),
+                          (kind == BAGPU_EDGE_STEREO) ? __ldg(D.o_ur + e) : 0.0, false, r0, r1, r2);
+            const double chi2 = r0 * (om * r0) + r1 * (om * r1) + r2 * (om * r2);
+            O.edge_chi2[e] = chi2;
+            double rho0 = chi2, rho1;
+            if (m & META_ROBUST) huber(chi2, kind == BAGPU_EDGE_STEREO ? D.delta_stereo : D.delta_mono, rho0, rho1);
+            chi_acc += rho0;
+        }
+    }
+    chi_acc = warp_allsum(chi_acc);
+    sc_acc = warp_allsum(sc_acc);
+    if (lane == 0) { s_chi[warp] = chi_acc; s_sc[warp] = sc_acc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0, s = 0.0;
+        for (int w = 0; w < ST_WARPS; w++) { c += s_chi[w]; s += s_sc[w]; }
+        O.part_chi2[blockIdx.x] = c;
+        O.part_scale[blockIdx.x] = s;
     }
 }
