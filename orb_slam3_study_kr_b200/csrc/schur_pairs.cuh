@@ -6,7 +6,7 @@
 //
 //   stage_kernel / stage_wide_kernel   landmark-major (lane = observation). Linearise, reduce the landmark's Hll / bl,
 //       factor Hll + lambda I = L L^T (3x3 Cholesky, in registers) and write per observation
-//         Z  = W L^-T                      (6x3; W = rho1 w B^T A is the Hpl block)   -> Z Z'^T = W (Hll+lambda I)^-1 W'^T
+//         Z  = W L^-T = [P^T Y; Y]         (6x3; W = rho1 w B^T A is the Hpl block; stored as Y (3x3) and X_l, P = -[X_l]x)
 //         Dr = [ w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 bl (6) ], B = M [-[X_l]x | I]    -> the per-camera sums (Hpp, bp, bs)
 //   pair_kernel    camera-pair-major. At upload the device lists, for every upper block (a, b) of the reduced system,
 //       the observation pairs (e_a, e_b) of the landmarks both cameras see, sorted by block (pair_plan_*). A warp takes
@@ -19,8 +19,8 @@
 #pragma once
 #include "ba_kernels.cuh"
 
-#define ZR_STRIDE 20                       // 18 used: 160-byte records = five 32-byte sectors, one 256-bit access each
-#define DR_STRIDE 20                       // 18 used: [w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 b_l (6)], five sectors
+#define ZR_STRIDE 12                       // Y (9) | X_l (3): 96-byte records = three 32-byte sectors, one 256-bit access each
+#define DR_STRIDE 16                       // 15 used: [w M^T M (6) | M^T g (3) | Y L^-1 b_l (3) | X_l (3)], four sectors
 #ifndef PK_CHUNK
 #define LM_STRIDE 12
 #define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
@@ -149,45 +149,43 @@ BA_DEV void lane_hll(const LaneEdge &E, double *r) {
 
 // write the Z and Dr records of observation e (free pose). Inactive (level-1) edges write exact zeros.
 BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *__restrict__ Zp, double *__restrict__ Dp) {
+    // B = M [P | I] with M = columns 3..5 of B (= Jn R_rl) and P = -[X_l]x, so the Hpl block is W = w B^T A = [P^T V; V] with the
+    // 3x3 V = w M^T A, and Z = W L^-T = [P^T Y; Y] with Y = V L^-T: 9 + 3 numbers per observation instead of 18. In the same way
+    // w B^T B = [P | I]^T N [P | I] with N = w M^T M (6), B^T g = [P^T m; m] with m = M^T g (3), and the Schur right-hand side
+    // term -Z L^-1 b_l = -[P^T q; q] with q = Y L^-1 b_l (3). pair_kernel / update_z_kernel rebuild what they need.
     const bool act = E.valid;
     const double *A = E.L.A, *B = E.L.B;
     double *zo = Zp + ZR_STRIDE * e, *dout = Dp + DR_STRIDE * e;
-    double z[ZR_STRIDE], bs[6];
+    double y[9], q[3];
 #pragma unroll
-    for (int a = 0; a < 6; a++) {
-        const double w0 = act ? E.wgt * (B[a] * A[0] + B[6 + a] * A[3] + B[12 + a] * A[6]) : 0.0;
-        const double w1 = act ? E.wgt * (B[a] * A[1] + B[6 + a] * A[4] + B[12 + a] * A[7]) : 0.0;
-        const double w2 = act ? E.wgt * (B[a] * A[2] + B[6 + a] * A[5] + B[12 + a] * A[8]) : 0.0;
-        const double z0 = w0 * F.i00;
-        const double z1 = (w1 - z0 * F.l10) * F.i11;
-        const double z2 = (w2 - z0 * F.l20 - z1 * F.l21) * F.i22;
-        z[3 * a] = z0; z[3 * a + 1] = z1; z[3 * a + 2] = z2;
-        bs[a] = -(z0 * F.c0 + z1 * F.c1 + z2 * F.c2);
+    for (int i = 0; i < 3; i++) {
+        const double v0 = act ? E.wgt * (B[3 + i] * A[0] + B[9 + i] * A[3] + B[15 + i] * A[6]) : 0.0;
+        const double v1 = act ? E.wgt * (B[3 + i] * A[1] + B[9 + i] * A[4] + B[15 + i] * A[7]) : 0.0;
+        const double v2 = act ? E.wgt * (B[3 + i] * A[2] + B[9 + i] * A[5] + B[15 + i] * A[8]) : 0.0;
+        const double y0 = v0 * F.i00;
+        const double y1 = (v1 - y0 * F.l10) * F.i11;
+        const double y2 = (v2 - y0 * F.l20 - y1 * F.l21) * F.i22;
+        y[3 * i] = y0; y[3 * i + 1] = y1; y[3 * i + 2] = y2;
+        q[i] = y0 * F.c0 + y1 * F.c1 + y2 * F.c2;
     }
-    z[18] = z[19] = 0.0;
-#pragma unroll
-    for (int i = 0; i < ZR_STRIDE / 4; i++) stg256(zo + 4 * i, z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
-    // B = M [ -[X_l]x | I ] (M = columns 3..5 of B), so w B^T B and B^T g follow from N = w M^T M (6), X_l (3) and M^T g (3):
-    // pair_kernel rebuilds the 27 values when it sums the records of a camera
-    double d[DR_STRIDE];
-    {
-        const double m00 = B[3], m01 = B[4], m02 = B[5], m10 = B[9], m11 = B[10], m12 = B[11], m20 = B[15], m21 = B[16], m22 = B[17];
-        d[0] = act ? E.wgt * (m00 * m00 + m10 * m10 + m20 * m20) : 0.0;
-        d[1] = act ? E.wgt * (m00 * m01 + m10 * m11 + m20 * m21) : 0.0;
-        d[2] = act ? E.wgt * (m00 * m02 + m10 * m12 + m20 * m22) : 0.0;
-        d[3] = act ? E.wgt * (m01 * m01 + m11 * m11 + m21 * m21) : 0.0;
-        d[4] = act ? E.wgt * (m01 * m02 + m11 * m12 + m21 * m22) : 0.0;
-        d[5] = act ? E.wgt * (m02 * m02 + m12 * m12 + m22 * m22) : 0.0;
-        d[6] = act ? E.L.xl[0] : 0.0; d[7] = act ? E.L.xl[1] : 0.0; d[8] = act ? E.L.xl[2] : 0.0;
-        d[9] = act ? (m00 * E.g0 + m10 * E.g1 + m20 * E.g2) : 0.0;
-        d[10] = act ? (m01 * E.g0 + m11 * E.g1 + m21 * E.g2) : 0.0;
-        d[11] = act ? (m02 * E.g0 + m12 * E.g1 + m22 * E.g2) : 0.0;
-    }
-#pragma unroll
-    for (int a = 0; a < 6; a++) d[12 + a] = bs[a];
-    d[18] = d[19] = 0.0;
-#pragma unroll
-    for (int i = 0; i < DR_STRIDE / 4; i++) stg256(dout + 4 * i, d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+    const double X0 = act ? E.L.xl[0] : 0.0, X1 = act ? E.L.xl[1] : 0.0, X2 = act ? E.L.xl[2] : 0.0;
+    stg256(zo, y[0], y[1], y[2], y[3]);
+    stg256(zo + 4, y[4], y[5], y[6], y[7]);
+    stg256(zo + 8, y[8], X0, X1, X2);
+    const double m00 = B[3], m01 = B[4], m02 = B[5], m10 = B[9], m11 = B[10], m12 = B[11], m20 = B[15], m21 = B[16], m22 = B[17];
+    const double n00 = act ? E.wgt * (m00 * m00 + m10 * m10 + m20 * m20) : 0.0;
+    const double n01 = act ? E.wgt * (m00 * m01 + m10 * m11 + m20 * m21) : 0.0;
+    const double n02 = act ? E.wgt * (m00 * m02 + m10 * m12 + m20 * m22) : 0.0;
+    const double n11 = act ? E.wgt * (m01 * m01 + m11 * m11 + m21 * m21) : 0.0;
+    const double n12 = act ? E.wgt * (m01 * m02 + m11 * m12 + m21 * m22) : 0.0;
+    const double n22 = act ? E.wgt * (m02 * m02 + m12 * m12 + m22 * m22) : 0.0;
+    const double g0 = act ? (m00 * E.g0 + m10 * E.g1 + m20 * E.g2) : 0.0;
+    const double g1 = act ? (m01 * E.g0 + m11 * E.g1 + m21 * E.g2) : 0.0;
+    const double g2 = act ? (m02 * E.g0 + m12 * E.g1 + m22 * E.g2) : 0.0;
+    stg256(dout, n00, n01, n02, n11);
+    stg256(dout + 4, n12, n22, g0, g1);
+    stg256(dout + 8, g2, q[0], q[1], q[2]);
+    stg256(dout + 12, X0, X1, X2, 0.0);
 }
 
 struct StageArgs {
@@ -326,19 +324,44 @@ struct PairArgs {
     double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit (only the Dr sums of the diagonal blocks)
 };
 
-// acc (6x6, row-major) += Z_x Z_y^T
+// P^T u for P = -[X]x: (-z u1 + y u2, z u0 - x u2, -y u0 + x u1)
+#define PT0(x, y, z, u0, u1, u2) (-(z) * (u1) + (y) * (u2))
+#define PT1(x, y, z, u0, u1, u2) ((z) * (u0) - (x) * (u2))
+#define PT2(x, y, z, u0, u1, u2) (-(y) * (u0) + (x) * (u1))
+
+// acc (6x6, row-major) += Z_x Z_y^T with Z = [P^T Y; Y]:  G = Y_x Y_y^T,  Z_x Z_y^T = [P_x^T G P_y, P_x^T G; G P_y, G]
 BA_DEV void pair_accumulate(const double *__restrict__ Z, int ex, int ey, double *acc) {
     const double *px = Z + ZR_STRIDE * (size_t)ex, *py = Z + ZR_STRIDE * (size_t)ey;
-    double x[ZR_STRIDE], y[ZR_STRIDE];
+    double a[ZR_STRIDE], b[ZR_STRIDE];
 #pragma unroll
-    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(py + 4 * i, y + 4 * i);
+    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(py + 4 * i, b + 4 * i);
 #pragma unroll
-    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(px + 4 * i, x + 4 * i);
+    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(px + 4 * i, a + 4 * i);
+    const double ax = a[9], ay = a[10], az = a[11], bx = b[9], by = b[10], bz = b[11];
+    double G[9], H[9];                                   // G = Y_a Y_b^T,  H = G P_b  (H[i][c] = (P_b^T applied to row i of G)[c])
 #pragma unroll
-    for (int r = 0; r < 6; r++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int c = 0; c < 6; c++)
-            acc[6 * r + c] += x[3 * r] * y[3 * c] + x[3 * r + 1] * y[3 * c + 1] + x[3 * r + 2] * y[3 * c + 2];
+        for (int k = 0; k < 3; k++) G[3 * i + k] = a[3 * i] * b[3 * k] + a[3 * i + 1] * b[3 * k + 1] + a[3 * i + 2] * b[3 * k + 2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        H[3 * i + 0] = PT0(bx, by, bz, G[3 * i], G[3 * i + 1], G[3 * i + 2]);
+        H[3 * i + 1] = PT1(bx, by, bz, G[3 * i], G[3 * i + 1], G[3 * i + 2]);
+        H[3 * i + 2] = PT2(bx, by, bz, G[3 * i], G[3 * i + 1], G[3 * i + 2]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // rotation rows (0..2): P_a^T applied to the columns of H (left block) and of G (right block)
+        acc[0 * 6 + c] += PT0(ax, ay, az, H[c], H[3 + c], H[6 + c]);
+        acc[1 * 6 + c] += PT1(ax, ay, az, H[c], H[3 + c], H[6 + c]);
+        acc[2 * 6 + c] += PT2(ax, ay, az, H[c], H[3 + c], H[6 + c]);
+        acc[0 * 6 + 3 + c] += PT0(ax, ay, az, G[c], G[3 + c], G[6 + c]);
+        acc[1 * 6 + 3 + c] += PT1(ax, ay, az, G[c], G[3 + c], G[6 + c]);
+        acc[2 * 6 + 3 + c] += PT2(ax, ay, az, G[c], G[3 + c], G[6 + c]);
+        // translation rows (3..5)
+        acc[3 * 6 + c] += H[c]; acc[4 * 6 + c] += H[3 + c]; acc[5 * 6 + c] += H[6 + c];
+        acc[3 * 6 + 3 + c] += G[c]; acc[4 * 6 + 3 + c] += G[3 + c]; acc[5 * 6 + 3 + c] += G[6 + c];
+    }
 }
 
 __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
@@ -383,8 +406,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
                 double v[DR_STRIDE];
 #pragma unroll
                 for (int q = 0; q < DR_STRIDE / 4; q++) ldg256(pd + 4 * q, v + 4 * q);
-                // w B^T B = [P | I]^T N [P | I] with P = -[X]x; T = N P, TL = P^T T
-                const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = v[6], y = v[7], z = v[8];
+                // v = N (6) | m (3) | q (3) | X (3).  w B^T B = [P | I]^T N [P | I] with P = -[X]x; T = N P, TL = P^T T
+                const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = v[12], y = v[13], z = v[14];
                 const double t00 = -z * n01 + y * n02, t01 = z * n00 - x * n02, t02 = -y * n00 + x * n01;
                 const double t10 = -z * n11 + y * n12, t11 = z * n01 - x * n12, t12 = -y * n01 + x * n11;
                 const double t20 = -z * n12 + y * n22, t21 = z * n02 - x * n22, t22 = -y * n02 + x * n12;
@@ -395,10 +418,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
                 d[11] += -y * t02 + x * t12;                                                              // TL(2,2)
                 d[12] += t02; d[13] += t12; d[14] += t22;
                 d[15] += n00; d[16] += n01; d[17] += n02; d[18] += n11; d[19] += n12; d[20] += n22;
-                d[21] += -z * v[10] + y * v[11]; d[22] += z * v[9] - x * v[11]; d[23] += -y * v[9] + x * v[10];   // B^T g = [P^T m; m]
-                d[24] += v[9]; d[25] += v[10]; d[26] += v[11];
-#pragma unroll
-                for (int q = 0; q < 6; q++) d[27 + q] += v[12 + q];
+                d[21] += PT0(x, y, z, v[6], v[7], v[8]); d[22] += PT1(x, y, z, v[6], v[7], v[8]); d[23] += PT2(x, y, z, v[6], v[7], v[8]);   // B^T g = [P^T m; m]
+                d[24] += v[6]; d[25] += v[7]; d[26] += v[8];
+                d[27] -= PT0(x, y, z, v[9], v[10], v[11]); d[28] -= PT1(x, y, z, v[9], v[10], v[11]); d[29] -= PT2(x, y, z, v[9], v[10], v[11]);   // -Z L^-1 b_l = -[P^T q; q]
+                d[30] -= v[9]; d[31] -= v[10]; d[32] -= v[11];
             }
 #pragma unroll
             for (int i = 0; i < 33; i++) red[i * PK_RED_LD + lane] = d[i];
@@ -505,13 +528,19 @@ __global__ void __launch_bounds__(ST_THREADS, 3) update_z_kernel(BaDev D, const 
         const int ip = in ? __ldg(D.o_pose + e) : 0;
         const int hx = valid ? __ldg(D.pose_hidx + ip) : -1;
         double r[3] = {0.0, 0.0, 0.0};
-        if (hx >= 0) {                                         // Z^T x_p
+        if (hx >= 0) {                                         // Z^T x_p = Y^T (P x_rot + x_trans), P = -[X_l]x
             double z[ZR_STRIDE];
 #pragma unroll
             for (int q = 0; q < ZR_STRIDE / 4; q++) ldg256(Zr + ZR_STRIDE * (size_t)e + 4 * q, z + 4 * q);
             const double *x = O.xp + 6 * hx;
-#pragma unroll
-            for (int a = 0; a < 6; a++) { const double xa = __ldg(x + a); r[0] += z[3 * a] * xa; r[1] += z[3 * a + 1] * xa; r[2] += z[3 * a + 2] * xa; }
+            const double x0 = __ldg(x), x1 = __ldg(x + 1), x2 = __ldg(x + 2);
+            const double X = z[9], Y = z[10], Zc = z[11];
+            const double v0 = Zc * x1 - Y * x2 + __ldg(x + 3);
+            const double v1 = -Zc * x0 + X * x2 + __ldg(x + 4);
+            const double v2 = Y * x0 - X * x1 + __ldg(x + 5);
+            r[0] = z[0] * v0 + z[3] * v1 + z[6] * v2;
+            r[1] = z[1] * v0 + z[4] * v1 + z[7] * v2;
+            r[2] = z[2] * v0 + z[5] * v1 + z[8] * v2;
         }
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
