@@ -21,9 +21,9 @@
 
 #define ZR_STRIDE 12                       // Y (9) | X_l (3): 96-byte records = three 32-byte sectors, one 256-bit access each
 #define DR_STRIDE 16                       // 15 used: [w M^T M (6) | M^T g (3) | Y L^-1 b_l (3) | X_l (3)], four sectors
-#ifndef PK_CHUNK
 #define LM_STRIDE 12
-#define PK_CHUNK 256                       // entries per work item (smaller chunks keep the concurrent working set in L2)
+#ifndef PK_CHUNK
+#define PK_CHUNK 512                       // entries per work item (per-item reductions vs the working set of the chunks in flight)
 #endif
 #ifndef PK_MINB
 #define PK_MINB 3
