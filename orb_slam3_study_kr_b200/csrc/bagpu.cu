@@ -139,6 +139,7 @@ struct bagpu_ctx {
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
     std::vector<int> h_hidx;
+    std::vector<int> h_colend, h_ce1, h_ce2, h_ceM;      // envelope arrays: kept alive, copied on the main stream without a sync
     double *pose_cur = nullptr, *pose_trial = nullptr, *pt_cur = nullptr, *pt_trial = nullptr;
     int n_sys = 0, ld = 0;
     int build_grid = 0;
@@ -245,6 +246,14 @@ __global__ void tw_scatter_kernel(int nM, int rT, int n, const double *__restric
     const double v = xM[k];
     y1[Ro] = v; y2[n - 1 - Ro] = v; x[Ro] = v;
 }
+// pos -> row and row -> pos: identity, or 0, nf-1, 1, nf-2, ... (two-way factorisation)
+__global__ void row_order_kernel(int nf, int zigzag, int *row_pos, int *row_of_pos) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nf) return;
+    int pos = a;
+    if (zigzag) { const int half = (nf + 1) / 2; pos = (a < half) ? 2 * a : 2 * (nf - 1 - a) + 1; }
+    row_pos[a] = pos; row_of_pos[pos] = a;
+}
 __global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, float *o) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = baf_atan2f(y[i], x[i]);
@@ -347,7 +356,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         // block the host until the watchdog fires.
         cudaFuncAttributes fa;
         const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
-                             (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel,
+                             (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel, (const void *)row_order_kernel,
                              (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel, (const void *)update_z_kernel,
                              (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel, (const void *)finish_trial_kernel,
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
@@ -434,26 +443,29 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     const bool dbg_t = getenv("BAGPU_DEBUG") != nullptr;
     auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tw0 = wall();
+    double lap_t = tw0; std::string laps;
+    auto lap = [&](const char *name) { if (dbg_t) { const double t = wall(); char buf[64]; snprintf(buf, sizeof(buf), " %s %.2f", name, t - lap_t); laps += buf; lap_t = t; } };
     // --- order: landmark-major, pose-ascending inside a landmark, insertion order preserved among equals
+    // one pass: order check AND (for the sorted case) the run boundaries lm_ptr[j] = first observation of landmark j
     std::atomic<bool> sorted_a{true};
+    std::vector<int> lm_ptr((size_t)Np + 1, -1);
     parallel_ranges(Ne, 1 << 16, [&](int, int64_t e0, int64_t e1) {
-        for (int64_t e = std::max<int64_t>(1, e0); e < e1; e++) {
-            const int a = p->obs_point[e - 1], b = p->obs_point[e];
-            if (a > b || (a == b && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted_a.store(false, std::memory_order_relaxed); break; }
+        for (int64_t e = e0; e < e1; e++) {
+            const int bpt = p->obs_point[e];
+            if (e == 0) { lm_ptr[(size_t)bpt] = 0; continue; }
+            const int apt = p->obs_point[e - 1];
+            if (apt != bpt) lm_ptr[(size_t)bpt] = (int)e;
+            if (apt > bpt || (apt == bpt && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted_a.store(false, std::memory_order_relaxed); break; }
         }
     });
     const bool sorted = sorted_a.load();
-    std::vector<int> lm_ptr((size_t)Np + 1, 0);
+    lap("check");
     if (sorted) {
-        // boundaries of the runs: lm_ptr[j] = first observation of landmark j; landmarks without observations inherit the next one
-        std::fill(lm_ptr.begin(), lm_ptr.end(), -1);
-        parallel_ranges(Ne, 1 << 16, [&](int, int64_t e0, int64_t e1) {
-            for (int64_t e = e0; e < e1; e++)
-                if (e == 0 || p->obs_point[e - 1] != p->obs_point[e]) lm_ptr[(size_t)p->obs_point[e]] = (int)e;
-        });
+        // landmarks without observations inherit the next one
         lm_ptr[(size_t)Np] = (int)Ne;
         for (int j = Np - 1; j >= 0; j--) if (lm_ptr[j] < 0) lm_ptr[j] = lm_ptr[j + 1];
     } else {
+        std::fill(lm_ptr.begin(), lm_ptr.end(), 0);
         for (int64_t e = 0; e < Ne; e++) lm_ptr[(size_t)p->obs_point[e] + 1]++;
         for (int j = 0; j < Np; j++) lm_ptr[j + 1] += lm_ptr[j];
     }
@@ -470,6 +482,24 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             }
     }
     ctx->identity_perm = sorted;
+    lap("lm_ptr");
+    // packed tasks / wide list (a serial greedy pass over the landmarks) on a helper thread, beside the envelope computation:
+    // tasks = runs of whole landmarks with <= 32 observations in total (stage_kernel, update kernels); a landmark with more
+    // than 32 observations is "wide" (stage_wide_kernel, update_kernel: warp = landmark)
+    std::vector<int2> tasks;
+    std::vector<int> wide_list;
+    struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } tasks_thread;
+    tasks_thread.t = std::thread([&tasks, &wide_list, &lm_ptr, Np] {
+        int tb = -1, tobs = 0;
+        tasks.reserve((size_t)Np / 2 + 16);
+        for (int j = 0; j <= Np; j++) {
+            const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
+            const bool brk = j == Np || k > 32;
+            if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
+            if (!brk) { if (tb < 0) tb = j; tobs += k; }
+            else if (j < Np) wide_list.push_back(j);
+        }
+    });
 
     // --- poses / free index
     CK(ctx->h_stage.ensure(sizeof(double) * 7 * (size_t)Nt + sizeof(double) * 7 * (size_t)std::max(1, p->n_rigs)));
@@ -500,6 +530,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_lm_ptr.p, lm_ptr.data(), sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
     h2d += sizeof(double) * (7 * (int64_t)Nt + 3 * (int64_t)Np) + sizeof(int) * ((int64_t)Nt + Np + 1);
 
+    lap("poses");
     // --- observations: raw arrays go up as they are; permutation and meta packing happen on the device
     const size_t ne = (size_t)Ne;
     CK(ctx->d_o_pose.ensure(4 * ne)); CK(ctx->d_o_point.ensure(4 * ne)); CK(ctx->d_o_meta.ensure(4 * ne));
@@ -557,6 +588,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_pt_init.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_meta_init.p, ctx->d_o_meta.p, 4 * ne, cudaMemcpyDeviceToDevice, st));
 
+    lap("obs-enqueue");
     const double tw1 = wall();
     // --- reduced camera system: envelope of Hschur from the landmark structure, band or dense storage
     const int n = 6 * nf;
@@ -593,11 +625,12 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaMemcpyAsync(lastrow.data(), ctx->d_colend.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
+        lap("lastrow");
         int bwb = 0;
         for (int h = 1; h < nf; h++) lastrow[h] = std::max(lastrow[h], lastrow[h - 1]);     // monotone: bounds the fill too
         for (int h = 0; h < nf; h++) bwb = std::max(bwb, lastrow[h] - h);
         ctx->band_blocks = bwb;
-        std::vector<int> col_end(std::max(1, n));
+        std::vector<int> &col_end = ctx->h_colend; col_end.assign(std::max(1, n), 0);
         int max_below = 0;
         int band = 6 * (bwb + 1);                            // max (i - j) + 1 inside the envelope ...
         for (int h = 0; h < nf; h++) for (int r = 0; r < 6; r++) col_end[6 * h + r] = 6 * lastrow[h] + 5;
@@ -611,7 +644,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid, &ctx->chol_maxr); if (rc2) return rc2; }
         // --- two-way factorisation: rows [0, rT) from the top, rows [n - rT, n) from the bottom (mirrored), separator M between
         ctx->tw = bagpu_ctx::TwoWay();
-        std::vector<int> ce1, ce2, ceM;
+        std::vector<int> &ce1 = ctx->h_ce1, &ce2 = ctx->h_ce2, &ceM = ctx->h_ceM;
         if (ctx->chol_maxr > 0 && !getenv("BAGPU_NO_TWOWAY") && !getenv("BAGPU_COMPARE") && !getenv("BAGPU_NO_TILES")) {
             int band_rows = 1;
             for (int j = 0; j < n; j++) band_rows = std::max(band_rows, std::min(n - 1, col_end[j]) - j + 1);
@@ -651,52 +684,33 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(ctx->d_colend1.ensure(4 * (size_t)T.n1)); CK(ctx->d_colend2.ensure(4 * (size_t)T.n2)); CK(ctx->d_colendM.ensure(4 * (size_t)T.nM));
             CK(ctx->d_y2.ensure(8 * (size_t)T.n2)); CK(ctx->d_SM.ensure(8 * T.sM_elems)); CK(ctx->d_rhsM.ensure(8 * (size_t)T.nM));
             CK(ctx->d_zeroM.ensure(8 * (size_t)T.nM)); CK(ctx->d_yM.ensure(8 * (size_t)T.nM)); CK(ctx->d_xM.ensure(8 * (size_t)T.nM));
-            CK(cudaMemcpyAsync(ctx->d_colend1.p, ce1.data(), 4 * (size_t)T.n1, cudaMemcpyHostToDevice, sp));
-            CK(cudaMemcpyAsync(ctx->d_colend2.p, ce2.data(), 4 * (size_t)T.n2, cudaMemcpyHostToDevice, sp));
-            CK(cudaMemcpyAsync(ctx->d_colendM.p, ceM.data(), 4 * (size_t)T.nM, cudaMemcpyHostToDevice, sp));
-            CK(cudaMemsetAsync(ctx->d_zeroM.p, 0, 8 * (size_t)T.nM, sp));
+            CK(cudaMemcpyAsync(ctx->d_colend1.p, ce1.data(), 4 * (size_t)T.n1, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_colend2.p, ce2.data(), 4 * (size_t)T.n2, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_colendM.p, ceM.data(), 4 * (size_t)T.nM, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(ctx->d_zeroM.p, 0, 8 * (size_t)T.nM, st));
             if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] two-way: k=%d rT=%d n1=%d n2=%d nM=%d ld=%d ldM=%d grids %d/%d/%d maxr %d/%d/%d\n",
                                                T.k, T.rT, T.n1, T.n2, T.nM, ctx->ld, T.ldM, T.grid1, T.grid2, T.gridM, T.maxr1, T.maxr2, T.maxrM);
         }
-        {   // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
-            std::vector<int> row_pos(std::max(1, nf)), row_of_pos(std::max(1, nf));
-            if (ctx->tw.on) { int lo = 0, hi = nf - 1, p2 = 0; while (lo <= hi) { row_of_pos[p2++] = lo++; if (lo <= hi) row_of_pos[p2++] = hi--; } }
-            else for (int h = 0; h < nf; h++) row_of_pos[h] = h;
-            for (int q = 0; q < nf; q++) row_pos[row_of_pos[q]] = q;
-            CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
-            CK(cudaMemcpyAsync(ctx->d_rowpos.p, row_pos.data(), 4 * (size_t)std::max(1, nf), cudaMemcpyHostToDevice, sp));
-            CK(cudaMemcpyAsync(ctx->d_rowofpos.p, row_of_pos.data(), 4 * (size_t)std::max(1, nf), cudaMemcpyHostToDevice, sp));
-            CK(cudaStreamSynchronize(sp));
-        }
-        const int occ_c = 0;
-        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d occ=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid, occ_c);
+        // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
+        // (built on the device: the plan stream must not queue H2D copies behind the bulk of the observation data)
+        CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
+        row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->tw.on ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
+        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
-        CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, sp));
-        CK(cudaStreamSynchronize(sp));                       // col_end is a stack vector
+        CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
     }
+    lap("envelope-tail");
     const double tw2 = wall();
     // --- plan of the linearise + Schur pass: packed tasks / wide list on the host (O(Np)), block-sorted pair lists on the device
     {
-        std::vector<int2> tasks;
-        std::vector<int> wide_list;
-        {
-            // tasks: runs of whole landmarks with <= 32 observations in total (stage_kernel, update_packed_kernel);
-            // a landmark with more than 32 observations is "wide" (stage_wide_kernel, update_kernel: warp = landmark)
-            int tb = -1, tobs = 0;
-            for (int j = 0; j <= Np; j++) {
-                const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
-                const bool brk = j == Np || k > 32;
-                if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
-                if (!brk) { if (tb < 0) tb = j; tobs += k; }
-                else if (j < Np) wide_list.push_back(j);
-            }
-        }
+        tasks_thread.t.join();
+        lap("tasks");
         const int nw = (int)wide_list.size();
         ctx->n_wide = nw; ctx->n_tasks = (int)tasks.size();
         CK(ctx->d_widelist.ensure(sizeof(int) * std::max<size_t>(1, wide_list.size())));
-        if (!wide_list.empty()) CK(cudaMemcpyAsync(ctx->d_widelist.p, wide_list.data(), sizeof(int) * wide_list.size(), cudaMemcpyHostToDevice, sp));
+        if (!wide_list.empty()) CK(cudaMemcpyAsync(ctx->d_widelist.p, wide_list.data(), sizeof(int) * wide_list.size(), cudaMemcpyHostToDevice, st));
         CK(ctx->d_tasks.ensure(sizeof(int2) * std::max<size_t>(1, tasks.size())));
-        if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, sp));
+        if (!tasks.empty()) CK(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, st));
         {
             int occ_u = 0, occ_st = 0, occ_sw = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, update_packed_kernel, ST_THREADS, 0));
@@ -743,6 +757,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaMemcpyAsync(&totals[0], pairoff + ne, 4, cudaMemcpyDeviceToHost, sp));
             CK(cudaMemcpyAsync(&totals[1], itemoff + nblk, 4, cudaMemcpyDeviceToHost, sp));
             CK(cudaStreamSynchronize(sp));
+            lap("count+scan+sync");
             const size_t npr = totals[0];
             if (npr >= (1ull << 31)) return fail(ctx, BAGPU_ERR_ARG, "too many observation pairs for one device shard (%zu)", npr);
             ctx->n_entries = (long long)npr; ctx->n_items = (int)totals[1];
@@ -777,7 +792,6 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
             CK(ctx->d_rowdone.ensure(sizeof(unsigned) * (size_t)std::max(1, nf)));
         }
-        CK(cudaStreamSynchronize(sp));                       // tasks / wide_list are stack vectors
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
                                            ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
@@ -796,6 +810,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(ctx->h_status.ensure(sizeof(double) * 32));
     ctx->pose_cur = ctx->d_pose_a.as<double>(); ctx->pose_trial = ctx->d_pose_b.as<double>();
     ctx->pt_cur = ctx->d_pt_a.as<double>(); ctx->pt_trial = ctx->d_pt_b.as<double>();
+    lap("plan-rest");
     const double tw3 = wall();
     CK(cudaEventRecord(ctx->ev_join, sp));
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));          // the plan stream joins the upload
@@ -804,6 +819,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_phase[0], ctx->ev_phase[1]);
     ctx->tm.h2d_ms = ms; ctx->tm.h2d_bytes = h2d;
+    if (dbg_t) fprintf(stderr, "[bagpu] upload laps:%s\n", laps.c_str());
     if (dbg_t) fprintf(stderr, "[bagpu] upload host ms: order+copies %.2f envelope %.2f plan %.2f tail+sync %.2f | stream %.2f\n", tw1 - tw0, tw2 - tw1, tw3 - tw2, wall() - tw3, ms);
     ctx->have_problem = true;
     return BAGPU_OK;
