@@ -292,6 +292,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         t = ctx.timing()
         e2e_passes += t["edge_linearisations"] + t["edge_evaluations"]
         h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
+        e2e_phase = {"upload_ms": t["h2d_ms"], "solve_ms": t["solve_ms"], "download_ms": t["d2h_ms"]}   # device-side phases of the last call
     e2e_value = sum_over_ranks(e2e_passes) / max_over_ranks(e2e_s)
 
     # ---- roofline of the linearise+Schur kernel
@@ -317,7 +318,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 "lm_iters_per_s": iters_per_s, "lm_iterations_per_step": acc["lm_iterations"] / args.steps,
                 "lm_trials_per_step": acc["lm_trials"] / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                 "e2e": {"value": e2e_value, "unit": "edge passes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                        "ms_per_step": 1e3 * e2e_s / args.steps, "phases_last_call": e2e_phase},
                 "gpu_launches": int(acc["total_launches"]),
                 "clocks": clk.summary(),
                 "roofline": {"kernel": "linearise+Schur pass: stage_kernel + pair_kernel (CUDA events around the two launches on the library stream; the band Cholesky runs beside pair_kernel on its own stream)", "bound": "hbm", "achieved": achieved, "peak": peak,
