@@ -7,13 +7,14 @@
 //   stage_kernel / stage_wide_kernel   landmark-major (lane = observation). Linearise, reduce the landmark's Hll / bl,
 //       factor Hll + lambda I = L L^T (3x3 Cholesky, in registers) and write per observation
 //         Z  = W L^-T = [P^T Y; Y]         (6x3; W = rho1 w B^T A is the Hpl block; stored as Y (3x3) and X_l, P = -[X_l]x)
-//         Dr = [ w M^T M (6) | X_l (3) | M^T g (3) | -Z L^-1 bl (6) ], B = M [-[X_l]x | I]    -> the per-camera sums (Hpp, bp, bs)
+//         Dr = [ w M^T M (6) | M^T g (3) | Y L^-1 bl (3) | X_l (3) ], B = M [-[X_l]x | I]   -> the per-camera sums (Hpp, bp, bs)
+//       and per landmark the factor L, L^-1 bl and bl (update_z_kernel back-substitutes from these, no second linearisation).
 //   pair_kernel    camera-pair-major. At upload the device lists, for every upper block (a, b) of the reduced system,
 //       the observation pairs (e_a, e_b) of the landmarks both cameras see, sorted by block (pair_plan_*). A warp takes
-//       one chunk of one block's list, each lane accumulates Z_a Z_b^T of its entries in 36 registers, the warp sums the
-//       lanes once and issues 36 REDs per chunk. The block is a contraction over its shared landmarks, so the work per
-//       entry is two 144-byte gathers (L2 resident: neighbouring blocks share the records) and 108 DFMA.
-//       Diagonal blocks also sum the Dr records of their camera (Hpp, bp, bs).
+//       one chunk of one block's list, each lane accumulates Z_a Z_b^T of its entries in 36 registers (G = Y_a Y_b^T, then
+//       [P_a^T G P_b, P_a^T G; G P_b, G]), the warp sums the lanes once and one total per block reaches S. The block is a
+//       contraction over its shared landmarks, so the work per entry is two 96-byte gathers (L2: neighbouring blocks share
+//       the records) and 81 + 27 MAC. Diagonal blocks also sum the Dr records of their camera (Hpp, bp, bs).
 //
 // Any track length, any number of edges on one (pose, point) pair and any camera span go through the same path.
 #pragma once
