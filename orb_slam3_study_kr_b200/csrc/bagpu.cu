@@ -1010,24 +1010,34 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             if (overlap) CK(cudaMemsetAsync(ctx->d_rowdone.p, 0, sizeof(unsigned) * (size_t)ctx->n_free, st));
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
             ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
-            // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator
-            auto enqueue_solver = [&](cudaStream_t sc, bool waits) -> int {
+            // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator.
+            // Two parts, so that the host can put stage_kernel / pair_kernel in the queue between them: the factorisation launches
+            // (which must be queued before the stage to own their SMs) and everything that runs after pair_kernel has ended anyway.
+            CholArgs c1, c2;
+            auto enqueue_solver_head = [&](cudaStream_t sc, bool waits) -> int {
                 if (waits) { ca.row_done = ctx->d_rowdone.as<unsigned>(); ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
                 if (!ctx->tw.on) { ctx->tm.total_launches++; return launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, sc); }
                 const bagpu_ctx::TwoWay &T = ctx->tw;
                 cudaStream_t s2 = ctx->stream_chol2;
-                CholArgs c1 = ca; c1.n = T.n1; c1.col_end = ctx->d_colend1.as<int>(); c1.p_stop = T.k;
-                CholArgs c2 = ca; c2.S = S2; c2.n = T.n2; c2.col_end = ctx->d_colend2.as<int>(); c2.y = ctx->d_y2.as<double>(); c2.p_stop = T.k;
+                c1 = ca; c1.n = T.n1; c1.col_end = ctx->d_colend1.as<int>(); c1.p_stop = T.k;
+                c2 = ca; c2.S = S2; c2.n = T.n2; c2.col_end = ctx->d_colend2.as<int>(); c2.y = ctx->d_y2.as<double>(); c2.p_stop = T.k;
                 c2.mirror_n = n; c2.wait_band = ld + 1;
                 CK(cudaEventRecord(ctx->ev_tw[0], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[0], 0));
                 int r = launch_chol(ctx, c1, T.grid1, T.maxr1, sc); if (r) return r;
                 r = launch_chol(ctx, c2, T.grid2, T.maxr2, s2); if (r) return r;
+                ctx->tm.total_launches += 2;
+                return BAGPU_OK;
+            };
+            auto enqueue_solver_tail = [&](cudaStream_t sc) -> int {
+                if (!ctx->tw.on) return BAGPU_OK;
+                const bagpu_ctx::TwoWay &T = ctx->tw;
+                cudaStream_t s2 = ctx->stream_chol2;
                 CK(cudaEventRecord(ctx->ev_tw[1], s2)); CK(cudaStreamWaitEvent(sc, ctx->ev_tw[1], 0));
                 tw_merge_kernel<<<grid_for((int64_t)T.nM * T.nM, 256), 256, 0, sc>>>(T.nM, T.rT, n, ld, S, S2, bp, bs, ctx->d_y.as<double>(), ctx->d_y2.as<double>(),
                                                                                   ctx->d_SM.as<double>(), T.ldM, ctx->d_rhsM.as<double>());
                 CholArgs cM; cM.S = ctx->d_SM.as<double>(); cM.n = T.nM; cM.ld = T.ldM; cM.lambda = lambda; cM.bp = ctx->d_rhsM.as<double>(); cM.bs = ctx->d_zeroM.as<double>();
                 cM.col_end = ctx->d_colendM.as<int>(); cM.y = ctx->d_yM.as<double>(); cM.dinv = ctx->d_dinv.as<double>(); cM.x = ctx->d_xM.as<double>(); cM.fail = ctx->d_fail.as<int>(); cM.prof = nullptr;
-                r = launch_chol(ctx, cM, T.gridM, T.maxrM, sc); if (r) return r;
+                int r = launch_chol(ctx, cM, T.gridM, T.maxrM, sc); if (r) return r;
                 tw_scatter_kernel<<<grid_for(T.nM, 128), 128, 0, sc>>>(T.nM, T.rT, n, ctx->d_xM.as<double>(), ctx->d_y.as<double>(), ctx->d_y2.as<double>(), ctx->d_xp.as<double>());
                 CK(cudaEventRecord(ctx->ev_tw[2], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[2], 0));
                 CholArgs b1 = c1; b1.p_stop = 0; b1.back_from = T.k; b1.row_done = nullptr;
@@ -1035,13 +1045,14 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 r = launch_chol(ctx, b1, 1, T.maxr1, sc); if (r) return r;
                 r = launch_chol(ctx, b2, 1, T.maxr2, s2); if (r) return r;
                 CK(cudaEventRecord(ctx->ev_tw[3], s2)); CK(cudaStreamWaitEvent(sc, ctx->ev_tw[3], 0));
-                ctx->tm.total_launches += 7;
+                ctx->tm.total_launches += 5;
                 return BAGPU_OK;
             };
             const int chol_sms = ctx->tw.on ? ctx->tw.grid1 + ctx->tw.grid2 : ctx->chol_grid;
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && !getenv("BAGPU_NO_TILES");
+            ScopedEv *ev_solve = nullptr;                     // overlap: the solve's timing bracket spans stage and pair on the other stream
             bool have_wide_part = false;
             int n_part_b = G, n_part_w = G;
             {
@@ -1052,8 +1063,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     if (overlap) {
                         CK(cudaEventRecord(ctx->ev_fork, st));
                         CK(cudaStreamWaitEvent(ctx->stream_chol, ctx->ev_fork, 0));
-                        { ScopedEv evc(ctx, EV_LINSOLVE, ctx->stream_chol); int rcc = enqueue_solver(ctx->stream_chol, true); if (rcc) return rcc; }
-                        CK(cudaEventRecord(ctx->ev_join, ctx->stream_chol));
+                        ev_solve = new ScopedEv(ctx, EV_LINSOLVE, ctx->stream_chol);
+                        int rcc = enqueue_solver_head(ctx->stream_chol, true); if (rcc) { delete ev_solve; return rcc; }
                     }
                     const int sm_avail = overlap ? std::max(1, ctx->n_sm - chol_sms) : ctx->n_sm;
                     const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
@@ -1074,6 +1085,12 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
                         pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
                         ctx->tm.total_launches++;
+                    }
+                    if (overlap) {                     // the rest of the solve goes into the queue behind the factorisations
+                        int rcc = enqueue_solver_tail(ctx->stream_chol);
+                        delete ev_solve; ev_solve = nullptr;
+                        if (rcc) return rcc;
+                        CK(cudaEventRecord(ctx->ev_join, ctx->stream_chol));
                     }
                 } else {
                     build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O);
@@ -1101,7 +1118,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             int rc = all_reduce_sum(ctx, S, sys_count); if (rc) return rc;
             if (overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             else if (n > 0) {
-                { ScopedEv ev(ctx, EV_LINSOLVE); rc = enqueue_solver(st, false); if (rc) return rc; }
+                { ScopedEv ev(ctx, EV_LINSOLVE); rc = enqueue_solver_head(st, false); if (rc) return rc; rc = enqueue_solver_tail(st); if (rc) return rc; }
             }
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
