@@ -1058,20 +1058,27 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             {
                 ScopedEv ev(ctx, EV_BUILD);
                 if (tiled) {
-                    // the Cholesky cluster is queued BEFORE stage_kernel: it takes its SMs now or as soon as the stage drains, in either
-                    // case ahead of pair_kernel; stage and pair leave those SMs alone (persistent grids sized for the rest)
-                    if (overlap) {
-                        CK(cudaEventRecord(ctx->ev_fork, st));
+                    // Host order: stage_kernel goes into the queue first and on all SMs; the factorisation clusters are queued right behind it
+                    // (their stream only waits for the memsets) and take their SMs as the stage drains, ahead of pair_kernel, which
+                    // cannot start before the stage has ended. BAGPU_STAGE_FIRST=0 queues the clusters before the stage instead.
+                    static const int stage_first = getenv("BAGPU_STAGE_FIRST") ? atoi(getenv("BAGPU_STAGE_FIRST")) : 2;
+                    auto start_solver = [&]() -> int {
                         CK(cudaStreamWaitEvent(ctx->stream_chol, ctx->ev_fork, 0));
                         ev_solve = new ScopedEv(ctx, EV_LINSOLVE, ctx->stream_chol);
-                        int rcc = enqueue_solver_head(ctx->stream_chol, true); if (rcc) { delete ev_solve; return rcc; }
+                        int rcc = enqueue_solver_head(ctx->stream_chol, true); if (rcc) { delete ev_solve; ev_solve = nullptr; }
+                        return rcc;
+                    };
+                    if (overlap) {
+                        CK(cudaEventRecord(ctx->ev_fork, st));
+                        if (!stage_first) { int rcc = start_solver(); if (rcc) return rcc; }
                     }
                     const int sm_avail = overlap ? std::max(1, ctx->n_sm - chol_sms) : ctx->n_sm;
-                    const int sgrid = std::max(1, std::min(ctx->stage_grid, sm_avail * ctx->stage_occ));
+                    const int sgrid = std::max(1, std::min(ctx->stage_grid, (stage_first == 2 ? ctx->n_sm : sm_avail) * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
                     SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
                     stage_kernel<<<sgrid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                     n_part_b = sgrid;
+                    if (overlap && stage_first) { int rcc = start_solver(); if (rcc) return rcc; }
                     if (ctx->n_wide > 0) {             // landmarks with more than 32 observations: warp = landmark
                         StageArgs SW = SA; SW.part_chi2 = part_chi_w;
                         stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
