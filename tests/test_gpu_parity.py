@@ -186,3 +186,30 @@ def test_solve_is_bitwise_reproducible(ctx):
     assert [t["chi2_after"] for t in a.trace] == [t["chi2_after"] for t in b.trace]
     assert np.array_equal(a.pose_qt, b.pose_qt) and np.array_equal(a.points, b.points)
     assert np.array_equal(a.edge_chi2, b.edge_chi2)
+
+
+def test_solver_variants_agree():
+    """The same map through the other code paths of the library (what the multi-GPU trial, a profiler run or a wide envelope
+    use): Cholesky after pair_kernel instead of beside it, one-way instead of two-way factorisation, re-linearising update,
+    v1 global-atomic build. Trajectories agree to 1e-9 relative; the trial counts are identical."""
+    import json
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_worker.py")
+
+    def run(extra):
+        env = dict(os.environ)
+        env.update(extra)
+        out = subprocess.run([sys.executable, worker], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    base = run({})
+    for extra in ({"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_NO_TWOWAY": "1"}, {"BAGPU_NO_OVERLAP": "1", "BAGPU_NO_TWOWAY": "1"},
+                  {"BAGPU_UPDATE_RELIN": "1"}, {"BAGPU_NO_TILES": "1"}, {"BAGPU_STAGE_FIRST": "0"}):
+        got = run(extra)
+        assert got["trials"] == base["trials"], (extra, got["trials"], base["trials"])
+        for a, b in zip(got["chi2"], base["chi2"]):
+            assert abs(a - b) <= 1e-9 * abs(b), (extra, a, b)
+        assert abs(got["pose_sum"] - base["pose_sum"]) <= 1e-9 * base["pose_sum"], extra
+        assert abs(got["point_sum"] - base["point_sum"]) <= 1e-9 * base["point_sum"], extra
