@@ -135,7 +135,7 @@ struct bagpu_ctx {
     DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone, d_Lm;
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, updz_grid = 1, parts_stride = 1;
     int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
-    size_t s_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
+    size_t s_elems = 0, scratch_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
     std::vector<int> h_hidx;
@@ -795,7 +795,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
                                            ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
-    CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n) + ctx->tw.s2_elems)));   // [S | bp | bs | S2 | hpp_diag]
+    // [S | bp | bs | S2 | trial scratch: y (n), y2 (n2), yM (nM), row_done (nf x u32), fail | hpp_diag]: one memset per trial covers S .. fail
+    ctx->scratch_elems = (size_t)std::max(1, n) + (size_t)ctx->tw.n2 + (size_t)ctx->tw.nM + ((size_t)std::max(1, nf) + 1) / 2 + 2;
+    CK(ctx->d_sys.ensure(sizeof(double) * (ctx->s_elems + 3 * (size_t)std::max(1, n) + ctx->tw.s2_elems + ctx->scratch_elems)));
     CK(ctx->d_xp.ensure(sizeof(double) * (size_t)std::max(1, n)));
     CK(ctx->d_y.ensure(sizeof(double) * (size_t)std::max(1, n)));
     CK(ctx->d_dinv.ensure(sizeof(double) * (size_t)std::max(1, n)));
@@ -940,8 +942,12 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
     const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid, PS = ctx->parts_stride;
     double *S = ctx->d_sys.as<double>();
-    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *S2 = bs + std::max(1, n), *hpp = S2 + ctx->tw.s2_elems;
-    const size_t sys_count = ctx->s_elems + 2 * (size_t)std::max(1, n) + ctx->tw.s2_elems;      // what a trial zeroes and all-reduces
+    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *S2 = bs + std::max(1, n);
+    const size_t sys_count = ctx->s_elems + 2 * (size_t)std::max(1, n) + ctx->tw.s2_elems;      // what a trial all-reduces
+    double *y1p = S2 + ctx->tw.s2_elems, *y2p = y1p + std::max(1, n), *yMp = y2p + ctx->tw.n2;  // trial scratch, zeroed with the system
+    unsigned *rowdone_p = reinterpret_cast<unsigned *>(yMp + ctx->tw.nM);
+    int *fail_p = reinterpret_cast<int *>(yMp + ctx->tw.nM + ((size_t)std::max(1, ctx->n_free) + 1) / 2);
+    double *hpp = S + sys_count + ctx->scratch_elems;
     double *parts = ctx->d_parts.as<double>();
     double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS,
            *part_chi_uw = parts + 5 * PS, *part_scale_w = parts + 6 * PS;
@@ -962,7 +968,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 ScopedEv ev(ctx, EV_BUILD);
                 StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
                 SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = 1.0; SA.part_chi2 = part_chi_b; SA.part_maxdiag = part_max;
-                SA.fail = ctx->d_fail.as<int>();
+                SA.fail = fail_p;
                 stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                 n_part0 = ctx->stage_grid;
                 if (ctx->n_wide > 0) {
@@ -996,10 +1002,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         bool first = true;
         do {
             // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
-            CK(cudaMemsetAsync(S, 0, sizeof(double) * sys_count, st));
-            CK(cudaMemsetAsync(ctx->d_fail.p, 0, sizeof(int), st));
-            CK(cudaMemsetAsync(ctx->d_y.p, 0, sizeof(double) * (size_t)std::max(1, n), st));
-            if (ctx->tw.on) { CK(cudaMemsetAsync(ctx->d_y2.p, 0, sizeof(double) * (size_t)ctx->tw.n2, st)); CK(cudaMemsetAsync(ctx->d_yM.p, 0, sizeof(double) * (size_t)ctx->tw.nM, st)); }
+            CK(cudaMemsetAsync(S, 0, sizeof(double) * (sys_count + ctx->scratch_elems), st));      // system + y, y2, yM, row_done, fail
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
             static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr ||
@@ -1007,20 +1010,19 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                                            getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
                                            getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr || getenv("CUDA_LAUNCH_BLOCKING") != nullptr;
             const bool overlap = !no_overlap && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
-            if (overlap) CK(cudaMemsetAsync(ctx->d_rowdone.p, 0, sizeof(unsigned) * (size_t)ctx->n_free, st));
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
-            ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = ctx->d_y.as<double>(); ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = ctx->d_fail.as<int>();
+            ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = y1p; ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = fail_p;
             // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator.
             // Two parts, so that the host can put stage_kernel / pair_kernel in the queue between them: the factorisation launches
             // (which must be queued before the stage to own their SMs) and everything that runs after pair_kernel has ended anyway.
             CholArgs c1, c2;
             auto enqueue_solver_head = [&](cudaStream_t sc, bool waits) -> int {
-                if (waits) { ca.row_done = ctx->d_rowdone.as<unsigned>(); ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
+                if (waits) { ca.row_done = rowdone_p; ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
                 if (!ctx->tw.on) { ctx->tm.total_launches++; return launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, sc); }
                 const bagpu_ctx::TwoWay &T = ctx->tw;
                 cudaStream_t s2 = ctx->stream_chol2;
                 c1 = ca; c1.n = T.n1; c1.col_end = ctx->d_colend1.as<int>(); c1.p_stop = T.k;
-                c2 = ca; c2.S = S2; c2.n = T.n2; c2.col_end = ctx->d_colend2.as<int>(); c2.y = ctx->d_y2.as<double>(); c2.p_stop = T.k;
+                c2 = ca; c2.S = S2; c2.n = T.n2; c2.col_end = ctx->d_colend2.as<int>(); c2.y = y2p; c2.p_stop = T.k;
                 c2.mirror_n = n; c2.wait_band = ld + 1;
                 CK(cudaEventRecord(ctx->ev_tw[0], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[0], 0));
                 int r = launch_chol(ctx, c1, T.grid1, T.maxr1, sc); if (r) return r;
@@ -1033,12 +1035,12 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 const bagpu_ctx::TwoWay &T = ctx->tw;
                 cudaStream_t s2 = ctx->stream_chol2;
                 CK(cudaEventRecord(ctx->ev_tw[1], s2)); CK(cudaStreamWaitEvent(sc, ctx->ev_tw[1], 0));
-                tw_merge_kernel<<<grid_for((int64_t)T.nM * T.nM, 256), 256, 0, sc>>>(T.nM, T.rT, n, ld, S, S2, bp, bs, ctx->d_y.as<double>(), ctx->d_y2.as<double>(),
+                tw_merge_kernel<<<grid_for((int64_t)T.nM * T.nM, 256), 256, 0, sc>>>(T.nM, T.rT, n, ld, S, S2, bp, bs, y1p, y2p,
                                                                                   ctx->d_SM.as<double>(), T.ldM, ctx->d_rhsM.as<double>());
                 CholArgs cM; cM.S = ctx->d_SM.as<double>(); cM.n = T.nM; cM.ld = T.ldM; cM.lambda = lambda; cM.bp = ctx->d_rhsM.as<double>(); cM.bs = ctx->d_zeroM.as<double>();
-                cM.col_end = ctx->d_colendM.as<int>(); cM.y = ctx->d_yM.as<double>(); cM.dinv = ctx->d_dinv.as<double>(); cM.x = ctx->d_xM.as<double>(); cM.fail = ctx->d_fail.as<int>(); cM.prof = nullptr;
+                cM.col_end = ctx->d_colendM.as<int>(); cM.y = yMp; cM.dinv = ctx->d_dinv.as<double>(); cM.x = ctx->d_xM.as<double>(); cM.fail = fail_p; cM.prof = nullptr;
                 int r = launch_chol(ctx, cM, T.gridM, T.maxrM, sc); if (r) return r;
-                tw_scatter_kernel<<<grid_for(T.nM, 128), 128, 0, sc>>>(T.nM, T.rT, n, ctx->d_xM.as<double>(), ctx->d_y.as<double>(), ctx->d_y2.as<double>(), ctx->d_xp.as<double>());
+                tw_scatter_kernel<<<grid_for(T.nM, 128), 128, 0, sc>>>(T.nM, T.rT, n, ctx->d_xM.as<double>(), y1p, y2p, ctx->d_xp.as<double>());
                 CK(cudaEventRecord(ctx->ev_tw[2], sc)); CK(cudaStreamWaitEvent(s2, ctx->ev_tw[2], 0));
                 CholArgs b1 = c1; b1.p_stop = 0; b1.back_from = T.k; b1.row_done = nullptr;
                 CholArgs b2 = c2; b2.p_stop = 0; b2.back_from = T.k; b2.row_done = nullptr;
@@ -1075,7 +1077,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     const int sm_avail = overlap ? std::max(1, ctx->n_sm - chol_sms) : ctx->n_sm;
                     const int sgrid = std::max(1, std::min(ctx->stage_grid, (stage_first == 2 ? ctx->n_sm : sm_avail) * ctx->stage_occ));
                     StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
-                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = ctx->d_fail.as<int>();
+                    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.lambda = lambda; SA.part_chi2 = part_chi_b; SA.part_maxdiag = nullptr; SA.fail = fail_p;
                     stage_kernel<<<sgrid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SA);
                     n_part_b = sgrid;
                     if (overlap && stage_first) { int rcc = start_solver(); if (rcc) return rcc; }
@@ -1085,7 +1087,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
                     }
                     if (ctx->n_items > 0) {
-                        PairArgs PA; PA.row_done = overlap ? ctx->d_rowdone.as<unsigned>() : nullptr;
+                        PairArgs PA; PA.row_done = overlap ? rowdone_p : nullptr;
                         PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1; PA.hpp_diag = nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                         PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
                         PA.S2 = ctx->tw.on ? S2 : nullptr; PA.n_tot = n; PA.n1 = ctx->tw.n1;
@@ -1162,7 +1164,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 TS.a[0] = part_chi_b; TS.na[0] = n_part_b; TS.b[0] = have_wide_part ? part_chi_w : nullptr; TS.nb[0] = n_part_w;
                 TS.a[1] = part_chi_u; TS.na[1] = n_part_u; TS.b[1] = upd_wide ? part_chi_uw : nullptr; TS.nb[1] = G;
                 TS.a[2] = part_scale; TS.na[2] = n_part_u; TS.b[2] = upd_wide ? part_scale_w : nullptr; TS.nb[2] = G;
-                TS.fail = ctx->d_fail.as<int>(); TS.out = dstat;
+                TS.fail = fail_p; TS.out = dstat;
                 finish_trial_kernel<<<3, 256, 0, st>>>(TS);
                 ctx->tm.total_launches++;
             }
