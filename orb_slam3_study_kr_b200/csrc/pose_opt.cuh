@@ -7,7 +7,12 @@
 #include <float.h>
 #include "ba_math.cuh"
 
+#ifndef PO_THREADS
 #define PO_THREADS 128
+#endif
+#ifndef PO_MINB
+#define PO_MINB 1
+#endif
 #define PO_WARPS (PO_THREADS / 32)
 
 struct PoseDev {
@@ -91,7 +96,7 @@ BA_DEV bool solve6(const double *H21 /*upper, row-major packed 21*/, double lamb
     return ok;
 }
 
-__global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(PoseDev D) {
+__global__ void __launch_bounds__(PO_THREADS, PO_MINB) pose_opt_kernel(PoseDev D) {
     __shared__ double sh[28][PO_WARPS];
     __shared__ double s_T[7];
     __shared__ int s_flag;
