@@ -24,14 +24,17 @@ shards = [synthetic.global_ba_shard(r, world, n_kf=n_kf, points_per_rank=ppr, ro
 mine = shards[rank]
 s = problem.schedule_merge_ba()            # two rounds + gate: exercises every collective
 got = ctx.solve_ba(mine, s)
+print(f"[rank {rank}] sharded solve done: {len(got.trace)} iterations", flush=True)   # progress markers: a time-out shows where it stopped
 
 ok = True
 if rank == 0:
     full = synthetic.concat_shards(shards)
     solo = api.Context(local)
     ref = solo.solve_ba(full, s)
+    print("[rank 0] single-GPU solve of the concatenated map done", flush=True)
     from oracle import ba_ref
     orc = ba_ref.solve(full, s)
+    print("[rank 0] oracle done", flush=True)
     assert len(got.trace) == len(ref.trace) == len(orc.trace), (len(got.trace), len(ref.trace), len(orc.trace))
     for a, b, c in zip(got.trace, ref.trace, orc.trace):
         assert a["trials"] == b["trials"] == c["trials"] and a["status"] == c["status"]
@@ -47,4 +50,7 @@ t = torch.from_numpy(got.pose_qt.copy()).cuda()
 t0 = t.clone(); dist.broadcast(t0, 0)
 assert torch.equal(t, t0), "poses differ across ranks"
 dist.barrier()
+print(f"[rank {rank}] poses agree across ranks", flush=True)
+solo = None
+ctx.close()
 dist.destroy_process_group()
