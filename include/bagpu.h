@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BAGPU_VERSION 1
+#define BAGPU_VERSION 2
 
 /* ---- status codes (SURVEY 8b "Errors") ---------------------------------- */
 #define BAGPU_OK                 0
@@ -136,6 +136,13 @@ typedef struct bagpu_trace {
     double  lambda;                 /* _currentLambda when solve() returns                  */
     int32_t trials;                 /* _levenbergIterations (qmax)                          */
     int32_t status;                 /* BAGPU_OK / BAGPU_TERMINATE_*                         */
+    /* per-iteration phase record (G2OBatchStatistics: numEdges, timeLinearize + timeQuadraticForm + timeSchurComplement,
+     * timeLinearSolver, timeUpdate + timeResiduals, timeIteration); device times from CUDA events, summed over the trials */
+    int64_t active_edges;           /* numEdges: level-0 edges of this round                */
+    double  linearise_schur_us;     /* stage_kernel + pair_kernel (all trials of the iteration) */
+    double  linear_solve_us;        /* reduced camera system; on one GPU it runs BESIDE pair_kernel, so the phases overlap */
+    double  update_us;              /* back-substitution, update, evaluation                 */
+    double  iteration_us;           /* host wall clock of the whole iteration                */
 } bagpu_trace;
 
 typedef struct bagpu_result {
@@ -188,7 +195,9 @@ typedef struct bagpu_timing {
     int64_t edge_evaluations;          /* active edges x evaluation passes                  */
     int64_t h2d_bytes, d2h_bytes;
     int32_t pcg_iterations;            /* total, when the PCG path ran                      */
-    int32_t schur_blocks;              /* upper-triangular 6x6 blocks of Hschur             */
+    int32_t schur_blocks;              /* upper-triangular 6x6 blocks of Hschur (inside the stored band) */
+    int32_t solve_retries;             /* trials re-run because the overlapped solve starved (see INTEGRATION.md "Threading") */
+    int32_t solver_parts;              /* partitions of the reduced-system factorisation (1 = one front, 2 = two-way, >2 = partitioned) */
 } bagpu_timing;
 
 typedef struct bagpu_ctx bagpu_ctx;

@@ -829,6 +829,7 @@ struct Engine {
                 bagpu_trace &t = res->trace[res->n_trace++];
                 t.round = round; t.iteration = it; t.chi2_before = iniChi; t.chi2_after = currentChi;
                 t.lambda = lambda; t.trials = qmax; t.status = st;
+                t.active_edges = 0; t.linearise_schur_us = t.linear_solve_us = t.update_us = t.iteration_us = 0.0;   // phase record: GPU library only
             }
             status = st;
             ok = (st == BAGPU_OK);

@@ -225,8 +225,8 @@ def local_bundle_adjustment(problem: BAProblem, stop_flag: Optional[np.ndarray] 
     `result.outliers(problem)` observations and writes poses/points back (src/Optimizer.cc:1410-1497)."""
     s = schedule_local_ba(inertial_map)
     s.stop_flag = stop_flag
-    if stop_flag is not None and stop_flag[0]:
-        raise BagpuError("stop flag already set: the reference returns before optimising (Optimizer.cc:1406-1408)")
+    # stop flag already set: the reference returns before optimising (Optimizer.cc:1406-1408). The library does the same:
+    # status BAGPU_STOPPED, empty trace, the (normalised) input estimates back -- no exception, as in the reference.
     return (ctx or default_context()).solve_ba(problem, s)
 
 

@@ -596,7 +596,7 @@ __global__ void finish_trial_kernel(TrialSums T) {
     }
     if (threadIdx.x == 0) {
         T.out[q] = sh[0];
-        if (q == 0) T.out[5] = (double)*T.fail;
+        if (q == 0) { const int wd = T.fail[1]; T.out[5] = wd ? (double)wd : (double)T.fail[0]; }   // fail[1]: starved wait (2 / 3), never a numerical verdict
     }
 }
 

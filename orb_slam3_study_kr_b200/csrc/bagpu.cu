@@ -104,9 +104,37 @@ constexpr int kPlanThreads = 8;
 
 }  // namespace
 
+// Development switches, read ONCE per context in bagpu_init (INTEGRATION.md lists them); none is needed in production.
+struct BagpuOptions {
+    bool debug = false;          // BAGPU_DEBUG: progress and timing lines on stderr
+    bool no_twoway = false;      // BAGPU_NO_TWOWAY: one factorisation front instead of two
+    bool compare = false;        // BAGPU_COMPARE: check the reduced system element-wise against the v1 global-atomic build
+    bool no_tiles = false;       // BAGPU_NO_TILES: v1 build_kernel / update_kernel instead of stage + pair
+    bool no_overlap = false;     // BAGPU_NO_OVERLAP (or a tool that serialises kernels is attached): solve after pair_kernel
+    int  stage_first = 2;        // BAGPU_STAGE_FIRST: launch order of stage_kernel and the factorisation clusters
+    bool update_relin = false;   // BAGPU_UPDATE_RELIN: re-linearising update kernel instead of update_z_kernel
+    bool no_band = false;        // BAGPU_NO_BAND: tiled chol_solve_kernel even for narrow envelopes
+    bool no_cluster = false;     // BAGPU_NO_CLUSTER: cooperative launch instead of one cluster for chol_solve_kernel
+    bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
+    int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
+    void read() {
+        auto on = [](const char *k) { return getenv(k) != nullptr; };
+        debug = on("BAGPU_DEBUG"); no_twoway = on("BAGPU_NO_TWOWAY"); compare = on("BAGPU_COMPARE"); no_tiles = on("BAGPU_NO_TILES");
+        // tools that serialise kernel launches (ncu, compute-sanitizer) would leave the Cholesky spinning on pair_kernel
+        no_overlap = on("BAGPU_NO_OVERLAP") || compare || no_tiles || on("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || on("CUDA_INJECTION64_PATH") ||
+                     on("NV_NSIGHT_INJECTION_PORT_BASE") || on("CUDA_LAUNCH_BLOCKING");
+        if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
+        update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
+        if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
+    }
+};
+
 struct bagpu_ctx {
     int device = 0;
     int n_sm = 148;
+    BagpuOptions opt;
+    size_t band_smem_cap = 200 * 1024;     // dynamic shared memory chol_band_kernel may use on this device
+    bool overlap_off = false;              // set when the overlapped solve starved once (watchdog): the solve then runs after pair_kernel
     cudaStream_t stream = nullptr;
     cudaStream_t stream_chol = nullptr;    // the band Cholesky runs beside pair_kernel on its own (high-priority) stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -337,6 +365,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
     if (device_id < 0) { if (cudaGetDevice(&device_id) != cudaSuccess) device_id = 0; }
     if (device_id >= ndev) { delete ctx; return BAGPU_ERR_NO_DEVICE; }
     ctx->device = device_id;
+    ctx->opt.read();
     if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return BAGPU_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
@@ -364,6 +393,17 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
                              (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
+        // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
+        // so a second context on another GPU of the same process gets its large dynamic shared memory and cluster sizes too.
+        if (cudaFuncGetAttributes(&fa, chol_band_kernel) == cudaSuccess) ctx->band_smem_cap = 232448 - fa.sharedSizeBytes - 1024;
+        bool ok_attr = true;
+        ok_attr &= cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem_cap) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        if (!ok_attr) { cudaGetLastError(); bagpu_destroy(ctx); return BAGPU_ERR_CUDA; }
     }
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     *out = ctx;
@@ -414,9 +454,9 @@ int bagpu_comm_init(bagpu_ctx *ctx, int world_size, int rank, const uint8_t id[1
     CK(cudaSetDevice(ctx->device));
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
-    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] ncclCommInitRank world %d dev %d ...\n", rank, world_size, ctx->device);
+    if (ctx->opt.debug) fprintf(stderr, "[bagpu r%d] ncclCommInitRank world %d dev %d ...\n", rank, world_size, ctx->device);
     CKN(g_nccl.CommInitRank(&ctx->comm, world_size, uid, rank));
-    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] ncclCommInitRank done\n", rank);
+    if (ctx->opt.debug) fprintf(stderr, "[bagpu r%d] ncclCommInitRank done\n", rank);
     ctx->world = world_size; ctx->rank = rank;
     return BAGPU_OK;
 }
@@ -440,7 +480,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     ctx->n_poses = Nt; ctx->n_points = Np; ctx->n_obs = Ne; ctx->n_cams = p->n_cameras; ctx->n_rigs = p->n_rigs;
     int64_t h2d = 0;
 
-    const bool dbg_t = getenv("BAGPU_DEBUG") != nullptr;
+    const bool dbg_t = ctx->opt.debug;
     auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tw0 = wall();
     double lap_t = tw0; std::string laps;
@@ -645,7 +685,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         // --- two-way factorisation: rows [0, rT) from the top, rows [n - rT, n) from the bottom (mirrored), separator M between
         ctx->tw = bagpu_ctx::TwoWay();
         std::vector<int> &ce1 = ctx->h_ce1, &ce2 = ctx->h_ce2, &ceM = ctx->h_ceM;
-        if (ctx->chol_maxr > 0 && !getenv("BAGPU_NO_TWOWAY") && !getenv("BAGPU_COMPARE") && !getenv("BAGPU_NO_TILES")) {
+        if (ctx->chol_maxr > 0 && !ctx->opt.no_twoway && !ctx->opt.compare && !ctx->opt.no_tiles) {
             int band_rows = 1;
             for (int j = 0; j < n; j++) band_rows = std::max(band_rows, std::min(n - 1, col_end[j]) - j + 1);
             const int k = (n - band_rows - CH_NB) / (2 * CH_NB);
@@ -688,14 +728,14 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaMemcpyAsync(ctx->d_colend2.p, ce2.data(), 4 * (size_t)T.n2, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(ctx->d_colendM.p, ceM.data(), 4 * (size_t)T.nM, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(ctx->d_zeroM.p, 0, 8 * (size_t)T.nM, st));
-            if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] two-way: k=%d rT=%d n1=%d n2=%d nM=%d ld=%d ldM=%d grids %d/%d/%d maxr %d/%d/%d\n",
+            if (ctx->opt.debug) fprintf(stderr, "[bagpu] two-way: k=%d rT=%d n1=%d n2=%d nM=%d ld=%d ldM=%d grids %d/%d/%d maxr %d/%d/%d\n",
                                                T.k, T.rT, T.n1, T.n2, T.nM, ctx->ld, T.ldM, T.grid1, T.grid2, T.gridM, T.maxr1, T.maxr2, T.maxrM);
         }
         // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
         // (built on the device: the plan stream must not queue H2D copies behind the bulk of the observation data)
         CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
         row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->tw.on ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
-        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid);
+        if (ctx->opt.debug) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
         CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
     }
@@ -784,15 +824,13 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(ctx->d_part.ensure(sizeof(double) * PK_PART * (size_t)std::max(1, ctx->n_items)));
             CK(ctx->d_blkdone.ensure(sizeof(unsigned) * ((size_t)nblk + 1)));
             CK(cudaMemsetAsync(ctx->d_blkdone.p, 0, sizeof(unsigned) * ((size_t)nblk + 1), sp));
-            static bool attr_set = false;
-            if (!attr_set) { CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES)); attr_set = true; }
             int occ_p = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, PK_THREADS, PK_SMEM_BYTES));
             ctx->pair_occ = std::max(1, occ_p);
             ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
             CK(ctx->d_rowdone.ensure(sizeof(unsigned) * (size_t)std::max(1, nf)));
         }
-        if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
+        if (ctx->opt.debug) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
                                            ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
     // [S | bp | bs | S2 | trial scratch: y (n), y2 (n2), yM (nM), row_done (nf x u32), fail | hpp_diag]: one memset per trial covers S .. fail
@@ -832,7 +870,7 @@ namespace {
 
 int all_reduce_sum(bagpu_ctx *ctx, double *buf, size_t count) {
     if (ctx->world <= 1) return BAGPU_OK;
-    if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu r%d] allreduce sum %zu\n", ctx->rank, count);
+    if (ctx->opt.debug) fprintf(stderr, "[bagpu r%d] allreduce sum %zu\n", ctx->rank, count);
     CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
     return BAGPU_OK;
 }
@@ -860,41 +898,23 @@ size_t chol_dyn_smem(int n) { return n <= CH_MAX_SMEM_N ? sizeof(double) * (size
 //    up to CH_CLUSTER_MAX CTAs as one cluster (hardware barrier), beyond that a cooperative launch.
 #define CH_CLUSTER_MAX 16
 size_t chol_band_smem_min(int maxr) { return sizeof(double) * 2 * (size_t)(maxr + CB_PAD) * CB_LD; }
-size_t chol_band_smem_cap() {
-    static size_t cap = 0;
-    if (!cap) {
-        cudaFuncAttributes fa;
-        cap = 200 * 1024;
-        if (cudaFuncGetAttributes(&fa, chol_band_kernel) == cudaSuccess) cap = 232448 - fa.sharedSizeBytes - 1024;
-    }
-    return cap;
-}
 // dynamic shared memory of the band kernel: the two block-column buffers of the factorisation, or -- when it still fits --
 // the right-hand side plus two prefetched panels for the backward substitution, whichever is larger
-size_t chol_band_smem(int n, int maxr) {
-    const size_t cap = chol_band_smem_cap();
+size_t chol_band_smem(const bagpu_ctx *ctx, int n, int maxr) {
+    const size_t cap = ctx->band_smem_cap;
     const size_t need = chol_band_smem_min(maxr);
     const size_t bs = (size_t)((maxr + 1) | 1);
     const size_t back = sizeof(double) * ((size_t)n + 2 * CH_NB * bs);
     const size_t back3 = sizeof(double) * ((size_t)n + 3 * CH_NB * bs);      // pipelined backward substitution: three panel buffers
     const size_t ysm = sizeof(double) * (size_t)n;
-    if (back3 <= cap && !getenv("BAGPU_NO_BACK3")) return std::max(need, back3);
+    if (back3 <= cap && !ctx->opt.no_back3) return std::max(need, back3);
     if (back <= cap) return std::max(need, back);
     if (ysm <= cap) return std::max(need, ysm);
     return need;
 }
 
 int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(chol_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
-        CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)));
-        CK(cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_band_smem_cap()));
-        CK(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
-    }
-    static const bool no_band = getenv("BAGPU_NO_BAND") != nullptr;
+    const bool no_band = ctx->opt.no_band;
     const int maxr = max_below + CH_NB;
     if (maxr <= CB_MAXR && !no_band) {
         int nc = 2;
@@ -914,7 +934,7 @@ int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *max
 
 int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr, cudaStream_t stream = nullptr) {
     if (!stream) stream = ctx->stream;
-    static const bool no_cluster = getenv("BAGPU_NO_CLUSTER") != nullptr;
+    const bool no_cluster = ctx->opt.no_cluster;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -922,7 +942,7 @@ int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr, cudaStream_t st
     cfg.gridDim = dim3(grid); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
     if (maxr > 0) {
         cfg.blockDim = dim3(CB_THREADS);
-        cfg.dynamicSmemBytes = chol_band_smem(a.n, maxr);
+        cfg.dynamicSmemBytes = chol_band_smem(ctx, a.n, maxr);
         CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr, (int)(cfg.dynamicSmemBytes / sizeof(double))));
         return BAGPU_OK;
     }
@@ -959,11 +979,13 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
     bool ok = true;
     for (int it = 0; it < iterations && !stop() && ok; it++) {
         double currentChi = 0, iniChi = 0;
+        const auto it_t0 = std::chrono::steady_clock::now();
+        const double ph0[3] = {ctx->tm.build_ms, ctx->tm.linsolve_ms, ctx->tm.update_ms};
         if (it == 0) {
             // computeLambdaInit: tau * max diagonal of Hpp and Hll (optimization_algorithm_levenberg.cpp:171-185)
             CK(cudaMemsetAsync(hpp, 0, sizeof(double) * std::max(1, n), st));
             int n_part0 = G;
-            if (n > 0 && ctx->n_items > 0 && !getenv("BAGPU_NO_TILES")) {
+            if (n > 0 && ctx->n_items > 0 && !ctx->opt.no_tiles) {
                 // the same stage / pair kernels as the trials (fixed summation order): Dr records, then the diagonal blocks only
                 ScopedEv ev(ctx, EV_BUILD);
                 StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
@@ -1000,16 +1022,14 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         }
         double rho = 0; int qmax = 0;
         bool first = true;
+        bool redo = false;
         do {
+            redo = false;
             // buildSystem + setLambda + Schur complement, scattered straight into the reduced system
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (sys_count + ctx->scratch_elems), st));      // system + y, y2, yM, row_done, fail
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
-            static const bool no_overlap = getenv("BAGPU_NO_OVERLAP") != nullptr || getenv("BAGPU_COMPARE") != nullptr || getenv("BAGPU_NO_TILES") != nullptr ||
-                                           // tools that serialise kernel launches (ncu, compute-sanitizer) would leave the Cholesky spinning
-                                           getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
-                                           getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr || getenv("CUDA_LAUNCH_BLOCKING") != nullptr;
-            const bool overlap = !no_overlap && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
+            const bool overlap = !ctx->opt.no_overlap && !ctx->overlap_off && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
             ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = y1p; ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = fail_p;
             // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator.
@@ -1053,7 +1073,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             const int chol_sms = ctx->tw.on ? ctx->tw.grid1 + ctx->tw.grid2 : ctx->chol_grid;
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
-            const bool tiled = n > 0 && !getenv("BAGPU_NO_TILES");
+            const bool tiled = n > 0 && !ctx->opt.no_tiles;
             ScopedEv *ev_solve = nullptr;                     // overlap: the solve's timing bracket spans stage and pair on the other stream
             bool have_wide_part = false;
             int n_part_b = G, n_part_w = G;
@@ -1063,7 +1083,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     // Host order: stage_kernel goes into the queue first and on all SMs; the factorisation clusters are queued right behind it
                     // (their stream only waits for the memsets) and take their SMs as the stage drains, ahead of pair_kernel, which
                     // cannot start before the stage has ended. BAGPU_STAGE_FIRST=0 queues the clusters before the stage instead.
-                    static const int stage_first = getenv("BAGPU_STAGE_FIRST") ? atoi(getenv("BAGPU_STAGE_FIRST")) : 2;
+                    const int stage_first = ctx->opt.stage_first;
                     auto start_solver = [&]() -> int {
                         CK(cudaStreamWaitEvent(ctx->stream_chol, ctx->ev_fork, 0));
                         ev_solve = new ScopedEv(ctx, EV_LINSOLVE, ctx->stream_chol);
@@ -1105,7 +1125,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     build_kernel<<<G, BUILD_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, O);
                 }
             }
-            if (tiled && getenv("BAGPU_COMPARE")) {      // debug: the same system through the global-atomic kernel, compared element-wise
+            if (tiled && ctx->opt.compare) {      // debug: the same system through the global-atomic kernel, compared element-wise
                 const size_t cnt = ctx->s_elems + 2 * (size_t)n;
                 std::vector<double> a(cnt), b2(cnt);
                 cudaStreamSynchronize(st);
@@ -1133,13 +1153,13 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);
             UpdateOut U; U.lambda = lambda; U.xp = ctx->d_xp.as<double>(); U.pose_trial = ctx->pose_trial; U.pt_trial = ctx->pt_trial;
             U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale; U.lm_list = nullptr; U.n_list = 0;
-            const bool packed = ctx->n_tasks > 0 && !getenv("BAGPU_NO_TILES");
+            const bool packed = ctx->n_tasks > 0 && !ctx->opt.no_tiles;
             int n_part_u = G; bool upd_wide = false;
             {
                 ScopedEv ev(ctx, EV_UPDATE);
                 if (packed) {
                     UpdateTasks K; K.tasks = ctx->d_tasks.as<int2>(); K.n_tasks = ctx->n_tasks;
-                    if (tiled && ctx->n_items > 0 && !getenv("BAGPU_UPDATE_RELIN")) {
+                    if (tiled && ctx->n_items > 0 && !ctx->opt.update_relin) {
                         // back-substitution from the Z records of this trial's stage (no second linearisation)
                         update_z_kernel<<<ctx->updz_grid, ST_THREADS, 0, st>>>(D, ctx->pt_cur, U, K, ctx->d_Z.as<double>(), ctx->d_Lm.as<double>());
                         n_part_u = ctx->updz_grid;
@@ -1174,8 +1194,21 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             double h[6];
             rc = read_status(ctx, h, 6); if (rc) return rc;
             const int failflag = (int)h[5];
+            if (failflag >= 2) {
+                // The factorisation clusters waited 2 s for pair_kernel's row counters: the device was starved (another context's
+                // burst, MPS, a tool serialising kernels), NOT a numerical failure. Never feed that into rho / lambda: re-run this
+                // trial with the solve queued after pair_kernel, and keep that order for the rest of this context's life.
+                if (overlap) {
+                    ctx->overlap_off = true; ctx->tm.solve_retries++;
+                    ctx->tm.edge_linearisations -= n_active; ctx->tm.edge_evaluations -= n_active;
+                    if (ctx->opt.debug) fprintf(stderr, "[bagpu] overlapped solve starved (flag %d): trial re-run with the solve after pair_kernel\n", failflag);
+                    redo = true;
+                    continue;
+                }
+                return fail(ctx, BAGPU_ERR_CUDA, "reduced-system solve reported a wait time-out (flag %d) without overlap", failflag);
+            }
             const bool ok2 = (failflag == 0);
-            if (getenv("BAGPU_DEBUG")) fprintf(stderr, "[bagpu] trial it=%d q=%d lambda=%.6e chi2 %.9e -> %.9e scale %.3e fail=%d%s\n", it, qmax, lambda, h[0], h[1], h[2] + h[4], failflag, failflag >= 2 ? " (WATCHDOG: the Cholesky waited 2 s for pair_kernel)" : "");
+            if (ctx->opt.debug) fprintf(stderr, "[bagpu] trial it=%d q=%d lambda=%.6e chi2 %.9e -> %.9e scale %.3e fail=%d\n", it, qmax, lambda, h[0], h[1], h[2] + h[4], failflag);
             if (first) { currentChi = h[0]; iniChi = currentChi; first = false; }
             double tempChi = ok2 ? h[1] : DBL_MAX;
             rho = currentChi - tempChi;
@@ -1196,7 +1229,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 ni *= 2;                                            // pop(): keep the current state; edge chi2 stay as evaluated
             }
             qmax++; ctx->tm.lm_trials++;
-        } while (rho < 0 && qmax < 10 && !stop());
+        } while (redo || (rho < 0 && qmax < 10 && !stop()));
         ctx->tm.lm_iterations++;
         int stt = BAGPU_OK;
         if (qmax == 10 || rho == 0) stt = BAGPU_TERMINATE_TRIALS;
@@ -1207,6 +1240,10 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
         if (res && res->trace && res->n_trace < s->max_trace) {
             bagpu_trace &t = res->trace[res->n_trace++];
             t.round = round; t.iteration = it; t.chi2_before = iniChi; t.chi2_after = currentChi; t.lambda = lambda; t.trials = qmax; t.status = stt;
+            t.active_edges = n_active;
+            t.linearise_schur_us = 1e3 * (ctx->tm.build_ms - ph0[0]); t.linear_solve_us = 1e3 * (ctx->tm.linsolve_ms - ph0[1]);
+            t.update_us = 1e3 * (ctx->tm.update_ms - ph0[2]);
+            t.iteration_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - it_t0).count();
         }
         status = stt;
         ok = (stt == BAGPU_OK);
@@ -1227,7 +1264,7 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
     ctx->tm.build_ms = ctx->tm.linsolve_ms = ctx->tm.update_ms = 0;
     ctx->tm.build_launches = ctx->tm.update_launches = ctx->tm.linsolve_launches = ctx->tm.total_launches = 0;
     ctx->tm.lm_iterations = ctx->tm.lm_trials = ctx->tm.edge_linearisations = ctx->tm.edge_evaluations = 0;
-    ctx->tm.pcg_iterations = 0; ctx->tm.schur_blocks = (int)std::min<long long>((long long)ctx->n_free * (ctx->n_free + 1) / 2, (long long)ctx->n_free * (ctx->band_blocks + 1));
+    ctx->tm.pcg_iterations = 0; ctx->tm.solve_retries = 0; ctx->tm.solver_parts = ctx->tw.on ? 2 : 1; ctx->tm.schur_blocks = (int)std::min<long long>((long long)ctx->n_free * (ctx->n_free + 1) / 2, (long long)ctx->n_free * (ctx->band_blocks + 1));
     CK(cudaEventRecord(ctx->ev_phase[0], st));
     if (r) { r->n_trace = 0; r->status = BAGPU_OK; }
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -1483,7 +1520,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     int tgrid = 1, tmaxr = 0;
     { int rc2 = chol_plan_grid(ctx, n, max_below, &tgrid, &tmaxr); if (rc2) return rc2; }
     CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
-    ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = getenv("BAGPU_DEBUG") ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
+    ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = ctx->opt.debug ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
     int rc = launch_chol(ctx, ca, tgrid, tmaxr);
     if (rc) return rc;
     int hf = 0;
@@ -1491,7 +1528,7 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemcpyAsync(&hf, df.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (fail_out) *fail_out = hf;
-    if (getenv("BAGPU_DEBUG")) {
+    if (ctx->opt.debug) {
         long long hp[24];
         cudaMemcpy(hp, (char *)df.p + 16, 192, cudaMemcpyDeviceToHost);
         if (tmaxr > 0 && hf) fprintf(stderr, "[bagpu] band chol FAILED at panel %lld (n=%d maxr=%d grid=%d)\n", hp[23] - 1, n, tmaxr, tgrid);

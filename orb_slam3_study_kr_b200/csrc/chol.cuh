@@ -37,7 +37,7 @@ struct CholArgs {
     double *y;                // [n] scratch (used when n > CH_MAX_SMEM_N)
     double *dinv;             // [n] scratch: 1 / L(j,j)
     double *x;                // [n] out
-    int *fail;                // set to 1 on a non-positive pivot
+    int *fail;                // [2]: fail[0] = 1 on a non-positive pivot; fail[1] = 2 / 3 when a wait for pair_kernel timed out
     long long *prof;          // optional [8] cycle counters (potrf, trsm, sync1, writeback+y, update, sync2, backward)
     // chol_band_kernel running BESIDE pair_kernel (single GPU): block column c is read once every work item of the camera
     // rows it covers has been accumulated. row_done[a] counts finished items of row a, item_off[a * bw1] is the first item
@@ -532,13 +532,13 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
                 const int pos = a.row_pos ? a.row_pos[cam] : cam;
                 const unsigned need = a.item_off[(size_t)(pos + 1) * a.bw1] - a.item_off[(size_t)pos * a.bw1];
                 // pair_kernel runs beside this kernel; if it cannot (a profiler serialising kernels, a starved device) give up after
-                // 2 s and report a failed solve instead of hanging: the LM loop treats it as a rejected trial
+                // 2 s and raise the starvation word fail[1] instead of hanging: the host re-runs the trial with the solve after pair_kernel
                 unsigned long long t_start = 0, t_now = 0;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
                 while (ld_acquire_gpu(a.row_done + cam) < need) {
                     __nanosleep(100);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-                    if (t_now - t_start > 2000000000ull) { atomicExch(a.fail, 2 + (a.mirror_n ? 1 : 0)); break; }
+                    if (t_now - t_start > 2000000000ull) { atomicExch(a.fail + 1, 2 + (a.mirror_n ? 1 : 0)); break; }   // own word: a later pivot failure on the incomplete system must not hide it
                 }
             }
             __syncthreads();

@@ -5,8 +5,21 @@
 // atan2f/sqrtf on double arguments (src/CameraModels/KannalaBrandt8.cpp:47-49). glibc's atan2f is not
 // correctly rounded (it differs from (float)atan2((double)y,(double)x) on ~16 % of inputs), so the GPU
 // must reproduce the same algorithm, with no FMA contraction, to get the same residuals.
-// tests/test_atan2f.py checks this file against libm's atan2f on the host (hundreds of millions of
-// samples were bit-identical when this was written) and against the device build on the GPU.
+// tests/test_oracle.py::test_fdlibm_atan2f_port_matches_libm checks this file against libm's atan2f on the host
+// (hundreds of millions of samples were bit-identical when this was written);
+// tests/test_gpu_parity.py::test_device_atan2f_is_libm_exact checks the device build on the GPU.
+//
+// The algorithm and its constants are fdlibm's (e_atan2f.c / s_atanf.c, "Conversion to float by Ian Lance Taylor,
+// Cygnus Support"), whose notice must be preserved:
+//
+//   ====================================================
+//   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+//
+//   Developed at SunPro, a Sun Microsystems, Inc. business.
+//   Permission to use, copy, modify, and distribute this
+//   software is freely granted, provided that this notice
+//   is preserved.
+//   ====================================================
 #pragma once
 #include <stdint.h>
 #include <string.h>

@@ -81,7 +81,9 @@ class CSchedule(C.Structure):
 
 class CTrace(C.Structure):
     _fields_ = [("round", C.c_int32), ("iteration", C.c_int32), ("chi2_before", C.c_double),
-                ("chi2_after", C.c_double), ("lambda_", C.c_double), ("trials", C.c_int32), ("status", C.c_int32)]
+                ("chi2_after", C.c_double), ("lambda_", C.c_double), ("trials", C.c_int32), ("status", C.c_int32),
+                ("active_edges", C.c_int64), ("linearise_schur_us", C.c_double), ("linear_solve_us", C.c_double),
+                ("update_us", C.c_double), ("iteration_us", C.c_double)]
 
 
 class CResult(C.Structure):
@@ -112,7 +114,8 @@ class CTiming(C.Structure):
                 ("total_launches", C.c_int64), ("lm_iterations", C.c_int64), ("lm_trials", C.c_int64),
                 ("edge_linearisations", C.c_int64), ("edge_evaluations", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("pcg_iterations", C.c_int32), ("schur_blocks", C.c_int32)]
+                ("pcg_iterations", C.c_int32), ("schur_blocks", C.c_int32),
+                ("solve_retries", C.c_int32), ("solver_parts", C.c_int32)]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -284,7 +287,9 @@ class BAResult:
     def finish(self, c: "CResult", trace):
         self.status = int(c.status)
         self.trace = [dict(round=t.round, iteration=t.iteration, chi2_before=t.chi2_before, chi2_after=t.chi2_after,
-                           lambda_=t.lambda_, trials=t.trials, status=t.status) for t in trace[: c.n_trace]]
+                           lambda_=t.lambda_, trials=t.trials, status=t.status, active_edges=t.active_edges,
+                           linearise_schur_us=t.linearise_schur_us, linear_solve_us=t.linear_solve_us, update_us=t.update_us,
+                           iteration_us=t.iteration_us) for t in trace[: c.n_trace]]
         return self
 
     def outliers(self, problem: BAProblem, gate_mono=GATE_MONO, gate_stereo=GATE_STEREO) -> np.ndarray:
