@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- global bundle adjustment (BASELINE.json config 4) on N B200s, one JSON line.
+"""bench.py -- global bundle adjustment on N B200s, one JSON line.
 
   python bench.py --gpus N --steps K --warmup W            libbagpu arm
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle restatement, 1 thread)
 
-Workload (config.workload): "C4 global BA": 500 keyframes (1 fixed), 200 000 landmarks and ~2.16 M stereo/mono
-observations PER GPU (weak scaling: the keyframes are common, every rank owns its own 200 k landmarks and all their
-observations), EuRoC intrinsics, seed 4, non-robust (LoopClosing's GBA call, src/LoopClosing.cc:2289), 20 LM iterations.
-A step = one Optimizer::GlobalBundleAdjustemnt call = optimize(20) from the initial estimates.
+Workload (config.workload), the same map at every N (STRONG scaling):
+  c5 (default)  BASELINE.json config 5: 5000 keyframes (1 fixed), 2 000 000 landmarks, ~20 M stereo/mono observations, EuRoC
+                intrinsics, seed 5, non-robust (LoopClosing's GBA call, src/LoopClosing.cc:2289), optimize(20). It fits one GPU,
+                so N=1 solves the whole map; at N>1 rank r owns the contiguous landmark range [r Np/N, (r+1) Np/N) (MapPoint ids
+                grow with the keyframe that created them, so a range is covisibility-local) and all of its observations.
+  c4            BASELINE.json config 4: 500 keyframes, 200 000 landmarks, ~2 M observations, seed 4, sharded the same way.
+The other workload is measured after the headline and reported under "also" (device-resident and end to end), so one run
+carries both strong-scaling curves. A step = one Optimizer::GlobalBundleAdjustemnt call = optimize(20) from the initial estimates.
 
   value   edge passes per second (edge linearisations + edge evaluations, summed over ranks) with the map resident in
           HBM, timed with CUDA events on the library's stream, max over ranks.
@@ -15,8 +19,12 @@ A step = one Optimizer::GlobalBundleAdjustemnt call = optimize(20) from the init
           problem, solve, D2H of poses / points / per-edge chi2 / flags inside the timed region.
   roofline  the linearise+Schur pass (stage_kernel + pair_kernel), the dominant kernel group of the library stream:
           algorithmic bytes per pass / mean pass duration (CUDA events around every pass in the timed region, on the
-          library's stream) against the measured HBM copy bandwidth. On one GPU the band Cholesky runs BESIDE pair_kernel
-          on a second stream, so the `kernels` shares overlap and sum to more than 1.
+          library's stream) against the measured HBM copy bandwidth; roofline_fp64 reports the same pass against the FP64
+          throughput measured on the device (the Schur products are FP64 work). On one GPU the band Cholesky
+          runs BESIDE pair_kernel on a second stream, so the `kernels` shares overlap and sum to more than 1.
+  parity_check  before the timed region every run solves a small map (config 4 at 1/10 size, merge schedule: two rounds and
+          a gate) sharded over the N ranks and compares rank 0's result with the CPU oracle (1e-6 on chi2 per iteration
+          and on the estimates, identical trial counts and edge levels): the multi-GPU path is checked where it is timed.
   local_ba  secondary lines (1 GPU): configs 1-3 through bagpu_solve_ba and the 1000-frame PoseOptimization batch, end to end.
 """
 from __future__ import annotations
@@ -37,11 +45,12 @@ if ROOT not in sys.path:
 
 METRIC = "global BA edge passes/s (LM linearisations + evaluations per second; LM iters/s alongside)"
 N_ITER = 20
+WORKLOADS = {"c5": (5, "C5 global BA (BASELINE config 5): 5000 KFs (1 fixed), 2M landmarks, %d observations, seed 5"),
+             "c4": (4, "C4 global BA (BASELINE config 4): 500 KFs (1 fixed), 200k landmarks, %d observations, seed 4")}
 
 
-def workload_name(n_obs: int) -> str:
-    return ("C4 global BA, weak-scaled: 500 KFs (1 fixed) common, 200k landmarks / %d observations per GPU, "
-            "seed 4, EuRoC stereo+mono, non-robust, optimize(%d)" % (n_obs, N_ITER))
+def workload_name(which: str, n_obs_total: int) -> str:
+    return (WORKLOADS[which][1] % n_obs_total) + ", EuRoC stereo+mono, non-robust, optimize(%d), strong-scaled over contiguous landmark ranges" % N_ITER
 
 
 # ----------------------------------------------------------------------------- distributed helpers (also used by tests)
@@ -137,17 +146,35 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def make_workload(rank: int, world: int):
+_FULL = {}
+
+
+def full_map(which: str, robust: bool = False):
     from orb_slam3_study_kr_b200 import synthetic
-    return synthetic.global_ba_shard(rank, world, robust=False)
+    key = (which, robust)
+    if key not in _FULL:
+        _FULL[key] = synthetic.config(WORKLOADS[which][0], robust=robust)
+    return _FULL[key]
 
 
-def algorithmic_bytes_per_build_launch(p, n_free: int) -> float:
-    """per observation 40 B (mono) / 48 B (stereo) read; per landmark 24 B read; the reduced camera
-    system written once: 288 B per upper 6x6 block + 48 B per camera (dense pattern: all Nc(Nc+1)/2 blocks)."""
+def make_workload(which: str, rank: int, world: int, robust: bool = False):
+    """Rank `rank`'s landmark range of the full map (the whole map at world == 1). Every rank generates the same seeded map
+    and keeps its slice, so the union over ranks is exactly the BASELINE config at every N."""
+    full = full_map(which, robust)
+    return (full if world == 1 else full.shard_by_landmark(rank, world)), full.n_obs
+
+
+def pass_algorithmic(p, n_free: int, schur_blocks: int):
+    """SURVEY.md 8(d). Bytes: per observation 40 B (mono) / 48 B (stereo) read; per landmark 24 B read; the reduced camera
+    system written once: 288 B per upper 6x6 block INSIDE the stored band (bagpu_timing.schur_blocks) + 48 B per camera.
+    FP64 work of the Schur products: sum over landmarks of 54 k + 108 k(k+1)/2 + 27 multiply-adds (k = track length)."""
     from orb_slam3_study_kr_b200.problem import EDGE_STEREO
     n_st = int((p.obs_kind == EDGE_STEREO).sum())
-    return 48.0 * n_st + 40.0 * (p.n_obs - n_st) + 24.0 * p.n_points + 288.0 * (n_free * (n_free + 1) / 2) + 48.0 * n_free
+    nbytes = 48.0 * n_st + 40.0 * (p.n_obs - n_st) + 24.0 * p.n_points + 288.0 * schur_blocks + 48.0 * n_free
+    k = np.bincount(p.obs_point, minlength=p.n_points).astype(np.float64)
+    k = k[k > 0]
+    mac = float((54.0 * k + 108.0 * k * (k + 1) / 2 + 27.0).sum())
+    return nbytes, 2.0 * mac
 
 
 def peaks():
@@ -162,15 +189,18 @@ def peaks():
 def run_reference(args, rank: int, world: int):
     """The reference's BA is single-threaded by construction (Thirdparty/g2o/CMakeLists.txt:48 G2O_USE_OPENMP OFF) and
     cannot be built here (no Eigen3/OpenCV), so this arm times the oracle restatement on one host core. Each step is a
-    bounded sample: `ref_iters` LM iterations of the same map."""
+    bounded sample: `ref_iters` LM iterations of the same (whole) map; the rate does not depend on N."""
     if rank != 0:
         return
     from orb_slam3_study_kr_b200.problem import schedule_global_ba
     from oracle import ba_ref
-    p = make_workload(0, 1)
-    s = schedule_global_ba(args.ref_iters)
-    for _ in range(min(args.warmup, 1)):
-        ba_ref.solve(p, schedule_global_ba(1))
+    which = args.workload
+    p, n_obs_total = make_workload(which, 0, 1)
+    ref_iters = args.ref_iters if args.ref_iters > 0 else (1 if which == "c5" else 4)
+    s = schedule_global_ba(ref_iters)
+    if which != "c5":
+        for _ in range(min(args.warmup, 1)):
+            ba_ref.solve(p, schedule_global_ba(1))
     tot_s, passes, iters = 0.0, 0, 0
     for _ in range(args.steps):
         _, c = ba_ref.solve(p, s, True)
@@ -179,14 +209,14 @@ def run_reference(args, rank: int, world: int):
         iters += c["lm_iterations"]
     v = passes / tot_s
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edge passes/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "lm_iters_per_s": iters / tot_s,
-            "config": {"workload": workload_name(p.n_obs),
-                       "sample": "%d of %d LM iterations per step, rank 0's shard (the rate does not depend on N)" % (args.ref_iters, N_ITER)},
+            "config": {"workload": workload_name(which, n_obs_total),
+                       "sample": "%d of %d LM iterations per step on the whole map, one host thread (the rate does not depend on N)" % (ref_iters, N_ITER)},
             "cpu_baseline": {"value": v, "unit": "edge passes/s", "cores": 1, "kind": "port",
-                             "sample": "%d steps x %d LM iterations of the C4 map, oracle/ba_ref.cpp -O3 -march=x86-64-v3, 1 thread "
-                                       "(reference g2o is built without OpenMP)" % (args.steps, args.ref_iters)},
+                             "sample": "%d steps x %d LM iterations of the %s map, oracle/ba_ref.cpp -O3 -march=x86-64-v3, 1 thread "
+                                       "(reference g2o is built without OpenMP)" % (args.steps, ref_iters, which.upper())},
             "e2e": {"value": v, "unit": "edge passes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -229,61 +259,76 @@ def local_ba_lines(ctx, l2_flush, reps: int = 5):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args, rank: int, world: int, local_rank: int):
-    import torch
-    from orb_slam3_study_kr_b200 import api
-    from orb_slam3_study_kr_b200.problem import BAResult, schedule_global_ba
+def parity_check(ctx, rank: int, world: int):
+    """A small map (config 4 at 1/10 size: 50 keyframes, 20k landmarks, ~200k observations; merge schedule = two rounds with a
+    gate, so every collective runs) sharded over the N ranks exactly like the timed workload, against the CPU oracle on rank 0."""
+    from orb_slam3_study_kr_b200 import synthetic
+    from orb_slam3_study_kr_b200.problem import schedule_merge_ba
+    full = synthetic.config(4, scale=0.1, robust=True)
+    mine = full if world == 1 else full.shard_by_landmark(rank, world)
+    s = schedule_merge_ba()
+    got = ctx.solve_ba(mine, s)
+    out = None
+    if rank == 0:
+        from oracle import ba_ref
+        ref = ba_ref.solve(full, s)
+        lo, hi = (0, full.n_points) if world == 1 else mine.truth["point_range"]
+        sel = slice(None) if world == 1 else mine.truth["obs_mask"]
+        same_len = len(got.trace) == len(ref.trace)
+        rel = max([abs(a["chi2_after"] - b["chi2_after"]) / abs(b["chi2_after"]) for a, b in zip(got.trace, ref.trace)] + [0.0])
+        trials_equal = same_len and all(a["trials"] == b["trials"] and a["status"] == b["status"] for a, b in zip(got.trace, ref.trace))
+        dpose = float(np.abs(got.pose_qt - ref.pose_qt).max())
+        dpts = float(np.abs(got.points - ref.points[lo:hi]).max())
+        levels_equal = bool(np.array_equal(got.edge_level, ref.edge_level[sel]))
+        out = {"ok": bool(trials_equal and rel <= 1e-6 and dpose < 1e-6 and dpts < 1e-6 and levels_equal),
+               "max_rel_chi2": rel, "max_abs_pose": dpose, "max_abs_point_rank0": dpts, "trials_equal": bool(trials_equal),
+               "edge_levels_equal": levels_equal, "lm_iterations": len(got.trace),
+               "map": "C4 at 1/10 size (%d observations), merge schedule, sharded over %d ranks, vs oracle/ba_ref on rank 0" % (full.n_obs, world)}
+    return out
 
-    torch.cuda.set_device(local_rank)
-    ctx = api.Context(local_rank)
-    if world > 1:
-        uid = ctx.comm_unique_id() if rank == 0 else None
-        uid = broadcast_bytes(uid, 128)
-        ctx.comm_init(world, rank, uid)
-    p = make_workload(rank, world)
+
+def measure(ctx, args, which: str, rank: int, world: int, l2_flush, steps: int, warmup: int, local_rank: int, clocks: bool):
+    """Device-resident and end-to-end timing of one workload; returns the pieces of the JSON line (rank-reduced)."""
+    from orb_slam3_study_kr_b200.problem import schedule_global_ba
+    p, n_obs_total = make_workload(which, rank, world)
     ctx.pin_problem(p)
     s = schedule_global_ba(N_ITER)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-
-    def l2_flush():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-
     # ---- device-resident arm
     ctx.upload(p)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         ctx.reset_resident()
         ctx.solve_resident(s, download=False)
     barrier()
     dev_ms = 0.0
     acc = dict(build_ms=0.0, linsolve_ms=0.0, update_ms=0.0, build_launches=0, linsolve_launches=0, update_launches=0,
-               total_launches=0, lm_iterations=0, lm_trials=0, edge_linearisations=0, edge_evaluations=0)
+               total_launches=0, lm_iterations=0, lm_trials=0, edge_linearisations=0, edge_evaluations=0, solve_retries=0)
     t_wall0 = time.perf_counter()
-    with ClockSampler(local_rank) as clk:
-        for _ in range(args.steps):
-            ctx.reset_resident()
-            l2_flush()
-            ctx.solve_resident(s, download=False)
-            t = ctx.timing()
-            dev_ms += t["solve_ms"]
-            for k in acc:
-                acc[k] += t[k]
-        barrier()
+    clk = ClockSampler(local_rank) if clocks else None
+    if clk:
+        clk.__enter__()
+    for _ in range(steps):
+        ctx.reset_resident()
+        l2_flush()
+        ctx.solve_resident(s, download=False)
+        t = ctx.timing()
+        dev_ms += t["solve_ms"]
+        for k in acc:
+            acc[k] += t[k]
+    barrier()
+    if clk:
+        clk.__exit__()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     dev_ms_max = max_over_ranks(dev_ms)
     passes_all = sum_over_ranks(acc["edge_linearisations"] + acc["edge_evaluations"])
-    value = passes_all / (dev_ms_max * 1e-3)
-    iters_per_s = acc["lm_iterations"] / (dev_ms_max * 1e-3)
+    timing_last = ctx.timing()
 
     # ---- end-to-end arm through bagpu_solve_ba with host buffers
     res_buf = ctx.alloc_result(p, s)                         # page-locked, reused: what a SLAM thread's adapter keeps
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(min(warmup, 2)):
         ctx.solve_ba(p, s, into=res_buf)
     barrier()
-    e2e_s = 0.0
-    e2e_passes = 0
-    h2d = d2h = 0
-    for _ in range(args.steps):
+    e2e_s, e2e_passes, h2d, d2h, e2e_phase = 0.0, 0, 0, 0, {}
+    for _ in range(steps):
         l2_flush()
         barrier()
         t0 = time.perf_counter()
@@ -294,51 +339,106 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
         e2e_phase = {"upload_ms": t["h2d_ms"], "solve_ms": t["solve_ms"], "download_ms": t["d2h_ms"]}   # device-side phases of the last call
     e2e_value = sum_over_ranks(e2e_passes) / max_over_ranks(e2e_s)
+    trace = res_buf[0].trace
+    return dict(p=p, n_obs_total=n_obs_total, acc=acc, dev_ms=dev_ms, dev_ms_max=dev_ms_max, wall_ms=wall_ms, passes_all=passes_all,
+                value=passes_all / (dev_ms_max * 1e-3), e2e_value=e2e_value, e2e_s=e2e_s, h2d=sum_over_ranks(h2d), d2h=sum_over_ranks(d2h),
+                e2e_phase=e2e_phase, clocks=clk.summary() if clk else None, timing_last=timing_last, trace=trace)
 
-    # ---- roofline of the linearise+Schur kernel
+
+def run_gpu(args, rank: int, world: int, local_rank: int):
+    import torch
+    from orb_slam3_study_kr_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    ctx = api.Context(local_rank)
+    if world > 1:
+        uid = ctx.comm_unique_id() if rank == 0 else None
+        uid = broadcast_bytes(uid, 128)
+        ctx.comm_init(world, rank, uid)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def l2_flush():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    parity = None if args.no_parity else parity_check(ctx, rank, world)
+    which = args.workload
+    m = measure(ctx, args, which, rank, world, l2_flush, args.steps, args.warmup, local_rank, clocks=True)
+    p, acc, steps = m["p"], m["acc"], args.steps
+
+    # ---- roofline of the linearise+Schur pass (this rank's share of the map)
     peak, peak_src = peaks()
-    alg_bytes = algorithmic_bytes_per_build_launch(p, p.n_free)
+    alg_bytes, alg_flops = pass_algorithmic(p, p.n_free, m["timing_last"]["schur_blocks"])
     build_avg_ms = acc["build_ms"] / max(1, acc["build_launches"])
     achieved = alg_bytes / (build_avg_ms * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "build_pass_traffic.json")
-    if os.path.exists(tf):
+    if os.path.exists(tf) and which == "c4" and world == 1:
         try:
             traffic = json.load(open(tf)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    fp64 = ctx.fp64_peak()
+
+    also = None
+    if not args.no_also:
+        other = "c4" if which == "c5" else "c5"
+        o = measure(ctx, args, other, rank, world, l2_flush, max(2, min(args.steps, 3)) if other == "c5" else args.steps, min(args.warmup, 3), local_rank, clocks=False)
+        osteps = max(2, min(args.steps, 3)) if other == "c5" else args.steps
+        also = {"workload": workload_name(other, o["n_obs_total"]), "value": o["value"], "unit": "edge passes/s", "steps": osteps,
+                "ms_per_step": o["dev_ms_max"] / osteps, "lm_iters_per_s": o["acc"]["lm_iterations"] / (o["dev_ms_max"] * 1e-3),
+                "lm_trials_per_step": o["acc"]["lm_trials"] / osteps,
+                "e2e": {"value": o["e2e_value"], "ms_per_step": 1e3 * o["e2e_s"] / osteps, "phases_last_call": o["e2e_phase"]},
+                "kernels_ms_per_step": {k: o["acc"][k + "_ms"] / osteps for k in ("build", "linsolve", "update")},
+                "solver_parts": o["timing_last"]["solver_parts"]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "edge passes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        dev_ms = m["dev_ms"]
+        line = {"metric": METRIC, "value": m["value"], "unit": "edge passes/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+                "ms_per_step": m["dev_ms_max"] / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(p.n_obs),
-                           "sharding": "landmarks per rank, NCCL all-reduce of the reduced camera system per LM trial" if world > 1 else "1 GPU",
+                "config": {"workload": workload_name(which, m["n_obs_total"]),
+                           "sharding": ("contiguous landmark range per rank (%d observations on rank 0), NCCL all-reduce of the reduced camera system per LM trial" % p.n_obs) if world > 1 else "1 GPU",
                            "l2": "flushed between steps (256 MiB write)", "timing": "CUDA events on the library stream, max over ranks"},
-                "lm_iters_per_s": iters_per_s, "lm_iterations_per_step": acc["lm_iterations"] / args.steps,
-                "lm_trials_per_step": acc["lm_trials"] / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                "e2e": {"value": e2e_value, "unit": "edge passes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": 1e3 * e2e_s / args.steps, "phases_last_call": e2e_phase},
+                "lm_iters_per_s": acc["lm_iterations"] / (m["dev_ms_max"] * 1e-3), "lm_iterations_per_step": acc["lm_iterations"] / steps,
+                "lm_trials_per_step": acc["lm_trials"] / steps, "wall_ms_per_step": m["wall_ms"] / steps,
+                "ms_per_trial": m["dev_ms_max"] / max(1, acc["lm_trials"]),
+                "e2e": {"value": m["e2e_value"], "unit": "edge passes/s", "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
+                        "ms_per_step": 1e3 * m["e2e_s"] / steps, "phases_last_call": m["e2e_phase"]},
                 "gpu_launches": int(acc["total_launches"]),
-                "clocks": clk.summary(),
+                "clocks": m["clocks"],
+                "parity_check": parity,
                 "roofline": {"kernel": "linearise+Schur pass: stage_kernel + pair_kernel (CUDA events around the two launches on the library stream; the band Cholesky runs beside pair_kernel on its own stream)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": build_avg_ms,
-                             "launches": int(acc["build_launches"])},
-                "kernels": {"build_ms_per_step": acc["build_ms"] / args.steps, "linsolve_ms_per_step": acc["linsolve_ms"] / args.steps,
-                            "update_ms_per_step": acc["update_ms"] / args.steps,
-                            "share_of_step": {k: acc[k + "_ms"] / dev_ms for k in ("build", "linsolve", "update")}}}
+                             "launches": int(acc["build_launches"]),
+                             "note": "bytes count the 6x6 blocks inside the stored band (%d), not the dense pattern" % m["timing_last"]["schur_blocks"]},
+                "roofline_fp64": {"kernel": "the same pass against the FP64 pipe (SURVEY 8d: max(bytes/BW, flops/peak))", "bound": "fp64",
+                                  "achieved": alg_flops / (build_avg_ms * 1e-3) / 1e12, "peak": fp64["dfma_tflops"], "unit": "TFLOP/s",
+                                  "frac": alg_flops / (build_avg_ms * 1e-3) / 1e12 / max(fp64["dfma_tflops"], 1e-9),
+                                  "algorithmic_flops_per_launch": alg_flops, "peak_source": "measured on this device by bagpu_test_fp64_peak (DFMA probe)",
+                                  "dmma_peak_tflops": fp64["dmma_tflops"],
+                                  "bound_time_ms": {"hbm": alg_bytes / (peak * 1e9) * 1e3, "fp64": alg_flops / (fp64["dfma_tflops"] * 1e12) * 1e3}},
+                "kernels": {"build_ms_per_step": acc["build_ms"] / steps, "linsolve_ms_per_step": acc["linsolve_ms"] / steps,
+                            "update_ms_per_step": acc["update_ms"] / steps,
+                            "share_of_step": {k: acc[k + "_ms"] / dev_ms for k in ("build", "linsolve", "update")},
+                            "solver_parts": m["timing_last"]["solver_parts"], "solve_retries": int(acc["solve_retries"])},
+                "per_iteration": [{k: t[k] for k in ("iteration", "trials", "chi2_after", "active_edges", "linearise_schur_us", "linear_solve_us", "update_us", "iteration_us")}
+                                  for t in m["trace"]],
+                "also": also}
         if world == 1 and not args.no_local:
             line["local_ba"] = local_ba_lines(ctx, l2_flush)
         # CPU baseline beside it (rank 0, N=1 only): a bounded sample of the same map on one host core
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ba_ref
-            _, c = ba_ref.solve(p, schedule_global_ba(args.ref_iters), True)
+            from orb_slam3_study_kr_b200.problem import schedule_global_ba
+            ref_iters = args.ref_iters if args.ref_iters > 0 else (2 if which == "c5" else 4)
+            _, c = ba_ref.solve(p, schedule_global_ba(ref_iters), True)
             v = (c["edge_linearisations"] + c["edge_evaluations"]) / c["seconds"]
             line["cpu_baseline"] = {"value": v, "unit": "edge passes/s", "cores": 1, "kind": "port",
                                     "lm_iters_per_s": c["lm_iterations"] / c["seconds"],
-                                    "sample": "%d LM iterations of the same C4 map (%.1f s), oracle/ba_ref.cpp, 1 thread; host has %d cores"
-                                              % (args.ref_iters, c["seconds"], os.cpu_count())}
+                                    "sample": "%d LM iterations of the same %s map (%.1f s), oracle/ba_ref.cpp, 1 thread; host has %d cores"
+                                              % (ref_iters, which.upper(), c["seconds"], os.cpu_count())}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -351,9 +451,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="bagpu", choices=["bagpu", "reference"])
-    ap.add_argument("--ref-iters", type=int, default=4, help="LM iterations per CPU sample")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-iters", type=int, default=0, help="LM iterations per CPU sample (0: 4 for c4; 1-2 for c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-local", action="store_true", help="skip the secondary local-BA / pose-batch lines")
+    ap.add_argument("--no-also", action="store_true", help="skip the other global-BA workload")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the (sharded) path before the timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -29,7 +29,7 @@ _LIB = None
 EXPORTS = ["bagpu_init", "bagpu_destroy", "bagpu_strerror", "bagpu_last_error", "bagpu_comm_unique_id",
            "bagpu_comm_init", "bagpu_pin_host", "bagpu_unpin_host", "bagpu_solve_ba", "bagpu_upload",
            "bagpu_solve_resident", "bagpu_download", "bagpu_reset_resident", "bagpu_pose_opt_batch", "bagpu_pose_upload",
-           "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f", "bagpu_test_solve"]
+           "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f", "bagpu_test_solve", "bagpu_test_fp64_peak"]
 
 
 class BagpuError(RuntimeError):
@@ -197,6 +197,13 @@ class Context:
         self._check(self.lib.bagpu_test_solve(self.h, len(b), ce.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p),
                                               b.ctypes.data_as(C.c_void_p), lam, x.ctypes.data_as(C.c_void_p), C.byref(f)))
         return x, bool(f.value)
+
+    def fp64_peak(self) -> dict:
+        """Measured FP64 throughput of the device in TFLOP/s (DFMA and FP64 MMA probes)."""
+        a, b = C.c_double(0), C.c_double(0)
+        self.lib.bagpu_test_fp64_peak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.bagpu_test_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value}
 
     def device_atan2f(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
         y = np.ascontiguousarray(y, np.float32)

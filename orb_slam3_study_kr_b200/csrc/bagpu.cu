@@ -282,6 +282,37 @@ __global__ void row_order_kernel(int nf, int zigzag, int *row_pos, int *row_of_p
     if (zigzag) { const int half = (nf + 1) / 2; pos = (a < half) ? 2 * a : 2 * (nf - 1 - a) + 1; }
     row_pos[a] = pos; row_of_pos[pos] = a;
 }
+// FP64 issue-rate probes for the roofline of the Schur pass (K3 is FP64-bound): 8 independent DFMA chains per
+// thread, and 8 independent m8n8k4 FP64 MMA accumulators per warp, whole device, timed with CUDA events by bagpu_test_fp64_peak.
+__global__ void __launch_bounds__(1024) fp64_dfma_probe_kernel(double *o, int iters, double seed) {
+    const double a = seed + threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-12;
+    double c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = k * 1e-3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = fma(a, b, c[k]);
+    }
+    double sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += c[k];
+    if (sum == 12345.678) o[blockIdx.x * blockDim.x + threadIdx.x] = sum;      // keeps the chains alive, never true
+}
+__global__ void __launch_bounds__(1024) fp64_dmma_probe_kernel(double *o, int iters, double seed) {
+    const double a = seed + threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-12;
+    double c[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) c[k] = 0.0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[2 * k]), "+d"(c[2 * k + 1]) : "d"(a), "d"(b));
+    }
+    double sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) sum += c[k];
+    if (sum == 12345.678) o[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
 __global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, float *o) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = baf_atan2f(y[i], x[i]);
@@ -386,7 +417,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         cudaFuncAttributes fa;
         const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
                              (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel, (const void *)row_order_kernel,
-                             (const void *)atan2f_test_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel, (const void *)update_z_kernel,
+                             (const void *)atan2f_test_kernel, (const void *)fp64_dfma_probe_kernel, (const void *)fp64_dmma_probe_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel, (const void *)update_z_kernel,
                              (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel, (const void *)finish_trial_kernel,
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
                              (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
@@ -1264,7 +1295,7 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
     ctx->tm.build_ms = ctx->tm.linsolve_ms = ctx->tm.update_ms = 0;
     ctx->tm.build_launches = ctx->tm.update_launches = ctx->tm.linsolve_launches = ctx->tm.total_launches = 0;
     ctx->tm.lm_iterations = ctx->tm.lm_trials = ctx->tm.edge_linearisations = ctx->tm.edge_evaluations = 0;
-    ctx->tm.pcg_iterations = 0; ctx->tm.solve_retries = 0; ctx->tm.solver_parts = ctx->tw.on ? 2 : 1; ctx->tm.schur_blocks = (int)std::min<long long>((long long)ctx->n_free * (ctx->n_free + 1) / 2, (long long)ctx->n_free * (ctx->band_blocks + 1));
+    ctx->tm.pcg_iterations = 0; ctx->tm.solve_retries = 0; ctx->tm.solver_parts = ctx->tw.on ? 2 : 1; { const long long nf = ctx->n_free, bw1 = std::min<long long>(nf, ctx->band_blocks + 1); ctx->tm.schur_blocks = (int)(nf * bw1 - bw1 * (bw1 - 1) / 2); }   // blocks (a, b), a <= b <= a + band_blocks
     CK(cudaEventRecord(ctx->ev_phase[0], st));
     if (r) { r->n_trace = 0; r->status = BAGPU_OK; }
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -1544,6 +1575,34 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
         }
     }
     dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
+    return BAGPU_OK;
+}
+
+// Measured FP64 peaks of this device (TFLOP/s, 2 flops per multiply-add): plain DFMA and the m8n8k4 FP64 MMA, each the best
+// of three launches that fill every SM with 1024 threads. bench.py reports the Schur pass against them.
+int bagpu_test_fp64_peak(bagpu_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+    if (!ctx || !dfma_tflops || !dmma_tflops) return BAGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf o;
+    const int blocks = 2 * ctx->n_sm, threads = 1024, iters = 4096;
+    CK(o.ensure(sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; which++)
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(e0, ctx->stream));
+            if (which == 0) fp64_dfma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(o.as<double>(), iters, 0.5);
+            else fp64_dmma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(o.as<double>(), iters, 0.5);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+            // DFMA: 8 fma per thread per iteration; MMA m8n8k4: 8 x 8 x 4 = 256 multiply-adds per warp instruction, 8 per iteration
+            const double mac = which == 0 ? (double)blocks * threads * iters * 8.0 : (double)blocks * (threads / 32) * iters * 8.0 * 256.0;
+            if (rep > 0) best[which] = std::max(best[which], 2.0 * mac / (ms * 1e-3) / 1e12);
+        }
+    ctx->ev_used = 0;
+    *dfma_tflops = best[0]; *dmma_tflops = best[1];
+    o.release();
     return BAGPU_OK;
 }
 

@@ -148,3 +148,41 @@ def test_world_size_2_gloo_sharding(tmp_path):
     outs = [pr.communicate(timeout=240)[0].decode() for pr in procs]
     for pr, o in zip(procs, outs):
         assert pr.returncode == 0, o
+
+
+def build_cpp_adapter(tmp_path):
+    """g++ tests/abi/adapter.cpp -lbagpu: a compiled consumer of include/bagpu.h, filled the way INTEGRATION.md does."""
+    exe = str(tmp_path / "adapter")
+    libdir = os.path.join(ROOT, "orb_slam3_study_kr_b200")
+    api.load_library()                                        # fails loudly if the library has not been built
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "adapter.cpp"), "-o", exe, "-L" + libdir, "-lbagpu",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_adapter_compiles_and_refuses_without_gpu(tmp_path):
+    """The C++ adapter links against the C ABI (no C++ types cross it); without a device bagpu_init reports
+    BAGPU_ERR_NO_DEVICE and nothing is computed."""
+    import json
+    import torch
+    exe = build_cpp_adapter(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_boundary.py")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 2 and "no CUDA device" in json.loads(out.stdout)["error"]
+
+
+def test_strong_scaled_bench_workload_is_a_partition_of_the_config():
+    """bench.py's N-rank workload: the union of the ranks' landmark ranges is exactly the full map (checked on config 4 at
+    1/20 size through the same code path)."""
+    p = synthetic.config(4, scale=0.05)
+    tot_obs = tot_pts = 0
+    for r in range(8):
+        sh = p.shard_by_landmark(r, 8)
+        tot_obs += sh.n_obs
+        tot_pts += sh.n_points
+        # MapPoint ids grow with the keyframe that created them: a contiguous landmark range touches a contiguous keyframe range
+        kfs = np.unique(sh.obs_pose)
+        assert kfs.max() - kfs.min() < p.n_poses // 8 + 2 * 40 + 2
+    assert (tot_obs, tot_pts) == (p.n_obs, p.n_points)

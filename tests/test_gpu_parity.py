@@ -169,8 +169,19 @@ def test_full_size_global_ba_properties(ctx):
     assert e1 < 0.5 * e0
 
 
+@pytest.mark.parametrize("robust,iters", [(False, 20), (True, 20), (False, 10)], ids=["nonrobust_20", "robust_20_Tracking2603", "nonrobust_10_LoopClosing2289"])
+def test_full_size_global_ba_matches_oracle(ctx, robust, iters):
+    """BASELINE config 4 at FULL size (500 KFs, 200k points, ~2.0M observations) against the oracle, non-robust and robust
+    (Tracking.cc:2603: GlobalBundleAdjustemnt(map, 20), bRobust; LoopClosing.cc:2289: 10 iterations, non-robust). The oracle
+    needs ~0.75 s per LM iteration on one core, so each case costs 10-20 s."""
+    p = synthetic.config(4, robust=robust)
+    assert p.n_poses == 500 and p.n_points == 200000 and 1.8e6 < p.n_obs < 2.3e6
+    s = problem.schedule_global_ba(iters)
+    assert_parity(p, ctx.solve_ba(p, s), ba_ref.solve(p, s))
+
+
 def test_quarter_size_global_ba_matches_oracle(ctx):
-    """Config 4 at 1/4 size (125 KFs, 50k points, ~0.5M observations): the largest case the oracle does in seconds."""
+    """Config 4 at 1/4 size (125 KFs, 50k points, ~0.5M observations)."""
     p = synthetic.config(4, scale=0.25, robust=False)
     s = problem.schedule_global_ba(10)
     assert_parity(p, ctx.solve_ba(p, s), ba_ref.solve(p, s))
