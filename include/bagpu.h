@@ -243,6 +243,8 @@ int  bagpu_test_atan2f(bagpu_ctx *ctx, const float *y, const float *x, float *ou
 /* (A + lambda I) x = b with the production solver; A dense symmetric row-major, col_end[j] = last nonzero row of column j
  * (monotone). fail_out = 1 when a pivot was not positive. */
 int  bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, double *x, int *fail_out);
+/* The same through the partitioned solver with `parts` factorisation fronts (>= 3; long keyframe chains). */
+int  bagpu_test_solve_parts(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, int parts, double *x, int *fail_out);
 
 /* Measured FP64 throughput of the device (TFLOP/s): plain DFMA and the m8n8k4 FP64 MMA; the denominators of the FP64 roofline. */
 int  bagpu_test_fp64_peak(bagpu_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

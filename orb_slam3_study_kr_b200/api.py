@@ -29,7 +29,7 @@ _LIB = None
 EXPORTS = ["bagpu_init", "bagpu_destroy", "bagpu_strerror", "bagpu_last_error", "bagpu_comm_unique_id",
            "bagpu_comm_init", "bagpu_pin_host", "bagpu_unpin_host", "bagpu_solve_ba", "bagpu_upload",
            "bagpu_solve_resident", "bagpu_download", "bagpu_reset_resident", "bagpu_pose_opt_batch", "bagpu_pose_upload",
-           "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f", "bagpu_test_solve", "bagpu_test_fp64_peak"]
+           "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f", "bagpu_test_solve", "bagpu_test_solve_parts", "bagpu_test_fp64_peak"]
 
 
 class BagpuError(RuntimeError):
@@ -188,14 +188,14 @@ class Context:
         self._check(self.lib.bagpu_get_timing(self.h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in CTiming._fields_}
 
-    def test_solve(self, A: np.ndarray, b: np.ndarray, col_end: np.ndarray, lam: float = 0.0):
-        """(A + lam I) x = b with the production reduced-system solver (unit-test hook)."""
+    def test_solve(self, A: np.ndarray, b: np.ndarray, col_end: np.ndarray, lam: float = 0.0, parts: int = 1):
+        """(A + lam I) x = b with the production reduced-system solver (unit-test hook); parts >= 3: the partitioned solver."""
         A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
         ce = np.ascontiguousarray(col_end, np.int32)
         x = np.zeros_like(b); f = C.c_int(0)
-        self.lib.bagpu_test_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
-        self._check(self.lib.bagpu_test_solve(self.h, len(b), ce.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p),
-                                              b.ctypes.data_as(C.c_void_p), lam, x.ctypes.data_as(C.c_void_p), C.byref(f)))
+        self.lib.bagpu_test_solve_parts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        self._check(self.lib.bagpu_test_solve_parts(self.h, len(b), ce.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p),
+                                                    b.ctypes.data_as(C.c_void_p), lam, parts, x.ctypes.data_as(C.c_void_p), C.byref(f)))
         return x, bool(f.value)
 
     def fp64_peak(self) -> dict:

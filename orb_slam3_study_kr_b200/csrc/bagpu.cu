@@ -27,6 +27,7 @@
 #include "ba_kernels.cuh"
 #include "schur_pairs.cuh"
 #include "chol.cuh"
+#include "chol_parts.cuh"
 #include "pose_opt.cuh"
 
 namespace {
@@ -129,6 +130,23 @@ struct BagpuOptions {
     }
 };
 
+// Partitioned band solver (chol_parts.cuh): host-side plan and buffers of one reduced camera system.
+struct PartPlan {
+    bool on = false;
+    int P = 0, w = 0, n = 0, ld = 0;
+    PartTable T;
+    int nc = 1, maxr = 0, n_max = 0;                     // cluster size, reach and largest sub-system of the factorisation launch
+    int nS = 0, ldM = 1, gridM = 1, maxrM = 0;           // separator system
+    int spike_ctas = 0, inv_panels = 0, gram_ctas = 0, apply_rows = 0;
+    std::vector<int> h_subce, h_seprow, h_ceM;           // kept alive: copied without a sync
+    std::vector<CholArgs> h_tab;                         // [0, P): factorisation, [P, 2P): backward substitution
+    DevBuf d_tab, d_subce, d_seprow, d_V, d_linv, d_Dp, d_Ep, d_gp, d_SM, d_rhsM, d_zeroM, d_yM, d_xM, d_ceM, d_dinvM;
+    void release() {
+        DevBuf *b[] = {&d_tab, &d_subce, &d_seprow, &d_V, &d_linv, &d_Dp, &d_Ep, &d_gp, &d_SM, &d_rhsM, &d_zeroM, &d_yM, &d_xM, &d_ceM, &d_dinvM};
+        for (DevBuf *x : b) x->release();
+    }
+};
+
 struct bagpu_ctx {
     int device = 0;
     int n_sm = 148;
@@ -146,6 +164,7 @@ struct bagpu_ctx {
         int grid1 = 1, maxr1 = 0, grid2 = 1, maxr2 = 0, gridM = 1, maxrM = 0;
         size_t s2_elems = 0, sM_elems = 0;
     } tw;
+    PartPlan parts;                        // more than two fronts (long keyframe chains)
     DevBuf d_colend1, d_colend2, d_colendM, d_y2, d_SM, d_rhsM, d_zeroM, d_yM, d_xM, d_rowpos, d_rowofpos;
     char err[512] = {0};
     // ---- communicator (multi-GPU global BA)
@@ -185,6 +204,21 @@ struct bagpu_ctx {
 };
 
 namespace {
+
+// where the pieces of d_sys live: [S | bp | bs | S2 | y (n) | y2 (n2) | yM (nM) | row_done (nf x u32) | fail (4 x i32) | hpp_diag (n)]
+struct SysLayout { double *S, *bp, *bs, *S2, *y1, *y2, *yM, *hpp; unsigned *row_done; int *fail; size_t sys_count; };
+SysLayout sys_layout(const bagpu_ctx *ctx) {
+    SysLayout L;
+    const size_t n1 = (size_t)std::max(1, ctx->n_sys);
+    L.S = ctx->d_sys.as<double>();
+    L.bp = L.S + ctx->s_elems; L.bs = L.bp + n1; L.S2 = L.bs + n1;
+    L.sys_count = ctx->s_elems + 2 * n1 + ctx->tw.s2_elems;                    // what a trial all-reduces
+    L.y1 = L.S2 + ctx->tw.s2_elems; L.y2 = L.y1 + n1; L.yM = L.y2 + ctx->tw.n2;
+    L.row_done = reinterpret_cast<unsigned *>(L.yM + ctx->tw.nM);
+    L.fail = reinterpret_cast<int *>(L.yM + ctx->tw.nM + ((size_t)std::max(1, ctx->n_free) + 1) / 2);
+    L.hpp = L.S + L.sys_count + ctx->scratch_elems;
+    return L;
+}
 
 int fail(bagpu_ctx *c, int code, const char *fmt, ...) {
     if (c) {
@@ -422,7 +456,9 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
                              (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
                              (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
-                             (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel};
+                             (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel,
+                             (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
+                             (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
         // so a second context on another GPU of the same process gets its large dynamic shared memory and cluster sizes too.
@@ -461,6 +497,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (ctx->stream_chol2) { cudaStreamSynchronize(ctx->stream_chol2); cudaStreamDestroy(ctx->stream_chol2); }
     { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
       for (DevBuf *x : tb) x->release(); }
+    ctx->parts.release();
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaStreamSynchronize(ctx->stream_chol);
@@ -496,7 +533,12 @@ int bagpu_pin_host(void *p, size_t bytes) { return cudaHostRegister(p, bytes, cu
 int bagpu_unpin_host(void *p) { return cudaHostUnregister(p) == cudaSuccess ? BAGPU_OK : BAGPU_ERR_CUDA; }
 
 // ------------------------------------------------------------------------------- upload
-namespace { int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out); }
+namespace {
+int chol_plan_grid(bagpu_ctx *ctx, int n, int max_below, int *grid_out, int *maxr_out);
+int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<int> &col_end, int want_parts, bool overlap_possible, cudaStream_t st);
+int parts_bind(bagpu_ctx *ctx, PartPlan &pp, double *S, double *bp, double *bs, double *y, double *x, double *dinv, int *failp,
+               const unsigned *row_done, const unsigned *item_off, int bw1, const int *row_pos, cudaStream_t st);
+}
 
 int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (!ctx) return BAGPU_ERR_ARG;
@@ -715,8 +757,14 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         { int rc2 = chol_plan_grid(ctx, n, max_below, &ctx->chol_grid, &ctx->chol_maxr); if (rc2) return rc2; }
         // --- two-way factorisation: rows [0, rT) from the top, rows [n - rT, n) from the bottom (mirrored), separator M between
         ctx->tw = bagpu_ctx::TwoWay();
+        ctx->parts.on = false;
         std::vector<int> &ce1 = ctx->h_ce1, &ce2 = ctx->h_ce2, &ceM = ctx->h_ceM;
         if (ctx->chol_maxr > 0 && !ctx->opt.no_twoway && !ctx->opt.compare && !ctx->opt.no_tiles) {
+            // long keyframe chains: more than two factorisation fronts (chol_parts.cuh)
+            int rcp = parts_plan(ctx, ctx->parts, n, ctx->ld, col_end, ctx->opt.parts, ctx->world == 1 && !ctx->opt.no_overlap && !ctx->overlap_off, st);
+            if (rcp) return rcp;
+        }
+        if (!ctx->parts.on && ctx->chol_maxr > 0 && !ctx->opt.no_twoway && !ctx->opt.compare && !ctx->opt.no_tiles) {
             int band_rows = 1;
             for (int j = 0; j < n; j++) band_rows = std::max(band_rows, std::min(n - 1, col_end[j]) - j + 1);
             const int k = (n - band_rows - CH_NB) / (2 * CH_NB);
@@ -765,7 +813,8 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
         // (built on the device: the plan stream must not queue H2D copies behind the bulk of the observation data)
         CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
-        row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->tw.on ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
+        if (ctx->parts.on) row_order_parts_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->parts.T, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
+        else row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->tw.on ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
         if (ctx->opt.debug) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
         CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
@@ -881,6 +930,12 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(ctx->h_status.ensure(sizeof(double) * 32));
     ctx->pose_cur = ctx->d_pose_a.as<double>(); ctx->pose_trial = ctx->d_pose_b.as<double>();
     ctx->pt_cur = ctx->d_pt_a.as<double>(); ctx->pt_trial = ctx->d_pt_b.as<double>();
+    if (ctx->parts.on) {
+        const SysLayout L = sys_layout(ctx);
+        int rcb = parts_bind(ctx, ctx->parts, L.S, L.bp, L.bs, L.y1, ctx->d_xp.as<double>(), ctx->d_dinv.as<double>(), L.fail,
+                             L.row_done, ctx->d_itemoff.as<unsigned>(), ctx->band_blocks + 1, ctx->d_rowpos.as<int>(), st);
+        if (rcb) return rcb;
+    }
     lap("plan-rest");
     const double tw3 = wall();
     CK(cudaEventRecord(ctx->ev_join, sp));
@@ -974,7 +1029,7 @@ int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr, cudaStream_t st
     if (maxr > 0) {
         cfg.blockDim = dim3(CB_THREADS);
         cfg.dynamicSmemBytes = chol_band_smem(ctx, a.n, maxr);
-        CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr, (int)(cfg.dynamicSmemBytes / sizeof(double))));
+        CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr, (int)(cfg.dynamicSmemBytes / sizeof(double)), (const CholArgs *)nullptr));
         return BAGPU_OK;
     }
     if (grid <= CH_CLUSTER_MAX && !no_cluster) {
@@ -988,17 +1043,178 @@ int launch_chol(bagpu_ctx *ctx, CholArgs &a, int grid, int maxr, cudaStream_t st
     return BAGPU_OK;
 }
 
+// ---- partitioned band solver: plan (which fronts, which buffers), bind (argument tables), enqueue
+void envelope_metrics(const std::vector<int> &ce, int off, int nn, int &band, int &max_below) {
+    band = 1; max_below = 0;
+    for (int j = 0; j < nn; j++) band = std::max(band, ce[off + j] - j + 1);
+    for (int p0 = 0; p0 < nn; p0 += CH_NB) {
+        const int nb = std::min(CH_NB, nn - p0);
+        const int rend = std::min(nn - 1, ce[off + p0 + nb - 1]);
+        max_below = std::max(max_below, rend - (p0 + nb) + 1);
+        band = std::max(band, rend - p0 + 1);
+    }
+}
+
+// Decide whether (and into how many fronts) to cut the band; on success pp.on, the partition table, the static device arrays and all
+// buffers are in place. want_parts: 0 = automatic (cost model below), 1 = never, >= 3 = that many (when the system is long enough).
+int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<int> &col_end, int want_parts, bool overlap_possible, cudaStream_t st) {
+    pp.on = false; pp.P = 0;
+    if (want_parts == 1 || want_parts == 2 || n < 32 * 24) return BAGPU_OK;
+    int band_rows = 1;
+    for (int j = 0; j < n; j++) band_rows = std::max(band_rows, std::min(n - 1, col_end[j]) - j + 1);
+    const int w = ((std::max(band_rows - 1, 32) + 95) / 96) * 96;       // separator rows: >= the reach of a column, boundaries on 16-camera / 3-panel marks
+    auto interior_of = [&](int P) { return ((n - (P - 1) * w) / P / 96) * 96; };
+    int P = 0;
+    if (want_parts >= 3) {
+        P = std::min(want_parts, PS_MAX_PARTS);
+        while (P >= 3 && interior_of(P) < std::max(w, 192)) P--;
+        if (P < 3) return BAGPU_OK;
+    } else {
+        // cost model (us; measured on B200: ~19 us per 32-column panel of the chain on long systems, ~20 us per separator panel in
+        // the tiled solver, ~0.3 ms of extra launches): fronts pay off from roughly 1000 keyframes on
+        const double panels = n / 32.0, two_way = panels / 2 * 19.0 + 250.0;
+        double best = 0.75 * two_way;
+        // beside pair_kernel the clusters take SMs away from it: stay within a quarter of the device there
+        const int p_cap = overlap_possible ? std::max(3, ctx->n_sm / 4 / 8) : PS_MAX_PARTS;
+        for (int q = 3; q <= std::min(PS_MAX_PARTS, p_cap); q++) {
+            const int per = interior_of(q);
+            if (per < std::max(2 * w, 576)) break;
+            const double c = (per / 32.0 + w / 32.0) * 19.0 + (q - 1) * (w / 32.0) * 20.0 + 300.0;
+            if (c < best) { best = c; P = q; }
+        }
+        if (P < 3) return BAGPU_OK;
+    }
+    const int per = interior_of(P);
+    PartTable &T = pp.T;
+    memset(&T, 0, sizeof(T));
+    T.P = P; T.w = w;
+    pp.h_subce.clear(); pp.h_seprow.clear();
+    long long v_off = 0, linv_off = 0;
+    int cta0 = 0, pan0 = 0, tile0 = 0, r = 0, maxr = 0, n_max = 0, apply_rows = 0;
+    const int nt = w / 32;
+    for (int i = 0; i < P; i++) {
+        PartDesc &D = T.d[i];
+        D.r0 = r;
+        D.m = (i + 1 < P) ? per : n - r;
+        D.k = (D.m + 31) / 32;
+        D.wT = (i > 0) ? w : 0; D.wB = (i + 1 < P) ? w : 0;
+        D.sep = i - 1;
+        D.v_off = v_off; D.linv_off = linv_off; D.ce_off = (int)pp.h_subce.size();
+        D.cta0 = cta0; D.pan0 = pan0; D.tile0 = tile0;
+        const int ni = D.m + D.wB;
+        for (int j = 0; j < ni; j++) pp.h_subce.push_back(std::min(std::min(n - 1, col_end[r + j]) - r, ni - 1));
+        int bnd, mb;
+        envelope_metrics(pp.h_subce, D.ce_off, ni, bnd, mb);
+        if (bnd - 1 > ld) return fail(ctx, BAGPU_ERR_ARG, "partition band %d exceeds the row stride %d", bnd, ld);
+        maxr = std::max(maxr, mb + CH_NB); n_max = std::max(n_max, ni);
+        if (i > 0) {
+            v_off += (long long)D.m * w; linv_off += (long long)D.k * 1024;
+            cta0 += (w + PS_NCOL - 1) / PS_NCOL; pan0 += D.k; tile0 += nt * (nt + 1) / 2 + nt * nt + 1; apply_rows += D.m;
+            pp.h_seprow.push_back(r - w);
+        }
+        r += D.m + D.wB;
+    }
+    if (maxr > CB_MAXR || ctx->opt.no_band) return BAGPU_OK;             // envelope too wide for the shared-memory window: keep the one-front solvers
+    int nc = 2;
+    while (nc * CH_NB < maxr) nc *= 2;
+    if (P * nc > ctx->n_sm) return BAGPU_OK;
+    pp.P = P; pp.w = w; pp.n = n; pp.ld = ld; pp.nc = nc; pp.maxr = maxr; pp.n_max = n_max;
+    pp.spike_ctas = cta0; pp.inv_panels = pan0; pp.gram_ctas = tile0; pp.apply_rows = apply_rows;
+    // separator system: block tridiagonal, (P - 1) blocks of w rows
+    pp.nS = (P - 1) * w;
+    pp.h_ceM.resize(pp.nS);
+    for (int j = 0; j < pp.nS; j++) pp.h_ceM[j] = std::min(pp.nS - 1, (j / w + 2) * w - 1);
+    int bM, mbM;
+    envelope_metrics(pp.h_ceM, 0, pp.nS, bM, mbM);
+    pp.ldM = std::max(1, std::min(bM - 1, pp.nS));
+    { int rc = chol_plan_grid(ctx, pp.nS, mbM, &pp.gridM, &pp.maxrM); if (rc) return rc; }
+    const size_t nS = (size_t)pp.nS, ww = (size_t)(P - 1) * w * w;
+    CK(pp.d_subce.ensure(4 * pp.h_subce.size())); CK(pp.d_seprow.ensure(4 * pp.h_seprow.size())); CK(pp.d_ceM.ensure(4 * nS));
+    CK(pp.d_V.ensure(8 * (size_t)std::max<long long>(1, v_off))); CK(pp.d_linv.ensure(8 * (size_t)std::max<long long>(1, linv_off)));
+    CK(pp.d_Dp.ensure(8 * ww)); CK(pp.d_Ep.ensure(8 * ww)); CK(pp.d_gp.ensure(8 * nS));
+    CK(pp.d_SM.ensure(8 * (nS * (pp.ldM + 1) + 8))); CK(pp.d_rhsM.ensure(8 * nS)); CK(pp.d_zeroM.ensure(8 * nS)); CK(pp.d_yM.ensure(8 * nS));
+    CK(pp.d_xM.ensure(8 * nS)); CK(pp.d_dinvM.ensure(8 * nS)); CK(pp.d_tab.ensure(sizeof(CholArgs) * 2 * (size_t)P));
+    CK(cudaMemcpyAsync(pp.d_subce.p, pp.h_subce.data(), 4 * pp.h_subce.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pp.d_seprow.p, pp.h_seprow.data(), 4 * pp.h_seprow.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pp.d_ceM.p, pp.h_ceM.data(), 4 * nS, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(pp.d_zeroM.p, 0, 8 * nS, st));
+    CK(cudaMemsetAsync(pp.d_SM.p, 0, 8 * (nS * (pp.ldM + 1) + 8), st));
+    CK(cudaMemsetAsync(pp.d_Ep.p, 0, 8 * ww, st));
+    pp.on = true;
+    if (ctx->opt.debug) fprintf(stderr, "[bagpu] partitioned solver: P=%d w=%d interior=%d (last %d) nc=%d maxr=%d | separator system n=%d ld=%d grid=%d maxr=%d | V %.1f MB\n",
+                                P, w, per, T.d[P - 1].m, nc, maxr, pp.nS, pp.ldM, pp.gridM, pp.maxrM, 8.0 * v_off / 1e6);
+    return BAGPU_OK;
+}
+
+// Argument tables of the two table launches (factorisation: one cluster per sub-system; backward substitution: one CTA each).
+int parts_bind(bagpu_ctx *ctx, PartPlan &pp, double *S, double *bp, double *bs, double *y, double *x, double *dinv, int *failp,
+               const unsigned *row_done, const unsigned *item_off, int bw1, const int *row_pos, cudaStream_t st) {
+    const int P = pp.P;
+    pp.h_tab.assign(2 * (size_t)P, CholArgs());
+    for (int i = 0; i < P; i++) {
+        const PartDesc &D = pp.T.d[i];
+        CholArgs a;
+        a.S = S + (size_t)D.r0 * pp.ld + D.r0; a.n = D.m + D.wB; a.ld = pp.ld; a.lambda = 0.0;
+        a.bp = bp + D.r0; a.bs = bs + D.r0; a.col_end = pp.d_subce.as<int>() + D.ce_off; a.y = y + D.r0; a.dinv = dinv + D.r0; a.x = x + D.r0;
+        a.fail = failp; a.prof = nullptr;
+        a.row_done = row_done; a.item_off = item_off; a.bw1 = bw1; a.row_pos = row_pos; a.row_base = D.r0;
+        a.p_stop = (i + 1 < P) ? D.k : 0; a.no_back = (i + 1 < P) ? 0 : 1;
+        pp.h_tab[i] = a;
+        CholArgs b = a;
+        b.row_done = nullptr; b.p_stop = 0; b.no_back = 0; b.back_from = D.k;
+        pp.h_tab[P + i] = b;
+    }
+    CK(cudaMemcpyAsync(pp.d_tab.p, pp.h_tab.data(), sizeof(CholArgs) * 2 * (size_t)P, cudaMemcpyHostToDevice, st));
+    return BAGPU_OK;
+}
+
+int parts_launch_table(bagpu_ctx *ctx, const PartPlan &pp, const CholArgs *table, int cluster, double lambda, const unsigned *wait, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(pp.P * cluster); cfg.blockDim = dim3(CB_THREADS); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = chol_band_smem(ctx, pp.n_max, pp.maxr);
+    CholArgs a; a.lambda = lambda; a.row_done = wait; a.S = nullptr; a.n = 0; a.ld = 0; a.bp = a.bs = nullptr; a.col_end = nullptr;
+    a.y = a.dinv = a.x = nullptr; a.fail = nullptr; a.prof = nullptr;
+    CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, pp.maxr, (int)(cfg.dynamicSmemBytes / sizeof(double)), table));
+    return BAGPU_OK;
+}
+// the P factorisation fronts (one launch); wait != nullptr: the clusters consume camera rows as pair_kernel completes them
+int parts_enqueue_factor(bagpu_ctx *ctx, const PartPlan &pp, double lambda, const unsigned *wait, cudaStream_t stream) {
+    return parts_launch_table(ctx, pp, pp.d_tab.as<CholArgs>(), pp.nc, lambda, wait, stream);
+}
+// spikes, separator system, backward substitutions
+int parts_enqueue_rest(bagpu_ctx *ctx, PartPlan &pp, const double *S, const double *bp, const double *bs, double *y, double *x, double lambda, int *failp, cudaStream_t st) {
+    const PartTable &T = pp.T;
+    const int nsep = pp.P - 1, w = pp.w;
+    panel_inverse_kernel<<<(pp.inv_panels + PS_INV_WARPS - 1) / PS_INV_WARPS, 32 * PS_INV_WARPS, 0, st>>>(T, S, pp.ld, pp.d_linv.as<double>(), pp.inv_panels);
+    spike_forward_kernel<<<pp.spike_ctas, PS_THREADS, 0, st>>>(T, S, pp.ld, pp.d_subce.as<int>(), pp.d_linv.as<double>(), pp.d_V.as<double>());
+    spike_gram_kernel<<<pp.gram_ctas, 256, 0, st>>>(T, S, pp.ld, pp.d_V.as<double>(), y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(), pp.d_gp.as<double>());
+    const long long na = (long long)nsep * w * 2 * w;
+    sep_assemble_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(nsep, w, pp.d_seprow.as<int>(), S, pp.ld, bp, bs, y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(),
+                                                                    pp.d_gp.as<double>(), pp.d_SM.as<double>(), pp.ldM, pp.d_rhsM.as<double>());
+    CK(cudaMemsetAsync(pp.d_yM.p, 0, 8 * (size_t)pp.nS, st));
+    CholArgs cM; cM.S = pp.d_SM.as<double>(); cM.n = pp.nS; cM.ld = pp.ldM; cM.lambda = lambda; cM.bp = pp.d_rhsM.as<double>(); cM.bs = pp.d_zeroM.as<double>();
+    cM.col_end = pp.d_ceM.as<int>(); cM.y = pp.d_yM.as<double>(); cM.dinv = pp.d_dinvM.as<double>(); cM.x = pp.d_xM.as<double>(); cM.fail = failp; cM.prof = nullptr;
+    { int rc = launch_chol(ctx, cM, pp.gridM, pp.maxrM, st); if (rc) return rc; }
+    sep_scatter_kernel<<<(nsep * w + 255) / 256, 256, 0, st>>>(nsep, w, pp.d_seprow.as<int>(), pp.d_xM.as<double>(), y, x);
+    spike_apply_kernel<<<(pp.apply_rows + 7) / 8, 256, 0, st>>>(T, pp.d_V.as<double>(), pp.d_xM.as<double>(), y, pp.apply_rows);
+    CK(cudaGetLastError());
+    return parts_launch_table(ctx, pp, pp.d_tab.as<CholArgs>() + pp.P, 1, lambda, nullptr, st);
+}
+
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
     cudaStream_t st = ctx->stream;
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
     const int n = ctx->n_sys, ld = ctx->ld, G = ctx->build_grid, PS = ctx->parts_stride;
-    double *S = ctx->d_sys.as<double>();
-    double *bp = S + ctx->s_elems, *bs = bp + std::max(1, n), *S2 = bs + std::max(1, n);
-    const size_t sys_count = ctx->s_elems + 2 * (size_t)std::max(1, n) + ctx->tw.s2_elems;      // what a trial all-reduces
-    double *y1p = S2 + ctx->tw.s2_elems, *y2p = y1p + std::max(1, n), *yMp = y2p + ctx->tw.n2;  // trial scratch, zeroed with the system
-    unsigned *rowdone_p = reinterpret_cast<unsigned *>(yMp + ctx->tw.nM);
-    int *fail_p = reinterpret_cast<int *>(yMp + ctx->tw.nM + ((size_t)std::max(1, ctx->n_free) + 1) / 2);
-    double *hpp = S + sys_count + ctx->scratch_elems;
+    const SysLayout L = sys_layout(ctx);
+    double *S = L.S, *bp = L.bp, *bs = L.bs, *S2 = L.S2;
+    const size_t sys_count = L.sys_count;                                                       // what a trial all-reduces
+    double *y1p = L.y1, *y2p = L.y2, *yMp = L.yM;                                               // trial scratch, zeroed with the system
+    unsigned *rowdone_p = L.row_done;
+    int *fail_p = L.fail;
+    double *hpp = L.hpp;
     double *parts = ctx->d_parts.as<double>();
     double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS,
            *part_chi_uw = parts + 5 * PS, *part_scale_w = parts + 6 * PS;
@@ -1069,6 +1285,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CholArgs c1, c2;
             auto enqueue_solver_head = [&](cudaStream_t sc, bool waits) -> int {
                 if (waits) { ca.row_done = rowdone_p; ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
+                if (ctx->parts.on) { ctx->tm.total_launches++; return parts_enqueue_factor(ctx, ctx->parts, lambda, waits ? rowdone_p : nullptr, sc); }
                 if (!ctx->tw.on) { ctx->tm.total_launches++; return launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, sc); }
                 const bagpu_ctx::TwoWay &T = ctx->tw;
                 cudaStream_t s2 = ctx->stream_chol2;
@@ -1082,6 +1299,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 return BAGPU_OK;
             };
             auto enqueue_solver_tail = [&](cudaStream_t sc) -> int {
+                if (ctx->parts.on) { ctx->tm.total_launches += 8; return parts_enqueue_rest(ctx, ctx->parts, S, bp, bs, y1p, ctx->d_xp.as<double>(), lambda, fail_p, sc); }
                 if (!ctx->tw.on) return BAGPU_OK;
                 const bagpu_ctx::TwoWay &T = ctx->tw;
                 cudaStream_t s2 = ctx->stream_chol2;
@@ -1101,7 +1319,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                 ctx->tm.total_launches += 5;
                 return BAGPU_OK;
             };
-            const int chol_sms = ctx->tw.on ? ctx->tw.grid1 + ctx->tw.grid2 : ctx->chol_grid;
+            const int chol_sms = ctx->parts.on ? ctx->parts.P * ctx->parts.nc : (ctx->tw.on ? ctx->tw.grid1 + ctx->tw.grid2 : ctx->chol_grid);
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && !ctx->opt.no_tiles;
@@ -1295,7 +1513,7 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
     ctx->tm.build_ms = ctx->tm.linsolve_ms = ctx->tm.update_ms = 0;
     ctx->tm.build_launches = ctx->tm.update_launches = ctx->tm.linsolve_launches = ctx->tm.total_launches = 0;
     ctx->tm.lm_iterations = ctx->tm.lm_trials = ctx->tm.edge_linearisations = ctx->tm.edge_evaluations = 0;
-    ctx->tm.pcg_iterations = 0; ctx->tm.solve_retries = 0; ctx->tm.solver_parts = ctx->tw.on ? 2 : 1; { const long long nf = ctx->n_free, bw1 = std::min<long long>(nf, ctx->band_blocks + 1); ctx->tm.schur_blocks = (int)(nf * bw1 - bw1 * (bw1 - 1) / 2); }   // blocks (a, b), a <= b <= a + band_blocks
+    ctx->tm.pcg_iterations = 0; ctx->tm.solve_retries = 0; ctx->tm.solver_parts = ctx->parts.on ? ctx->parts.P : (ctx->tw.on ? 2 : 1); { const long long nf = ctx->n_free, bw1 = std::min<long long>(nf, ctx->band_blocks + 1); ctx->tm.schur_blocks = (int)(nf * bw1 - bw1 * (bw1 - 1) / 2); }   // blocks (a, b), a <= b <= a + band_blocks
     CK(cudaEventRecord(ctx->ev_phase[0], st));
     if (r) { r->n_trace = 0; r->status = BAGPU_OK; }
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -1520,6 +1738,10 @@ int bagpu_get_timing(const bagpu_ctx *ctx, bagpu_timing *out) {
 
 // Unit-test hook for the reduced-system solver: dense symmetric A (row-major), envelope col_end, (A + lambda I) x = b.
 int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, double *x, int *fail_out) {
+    return bagpu_test_solve_parts(ctx, n, col_end, A, b, lambda, 1, x, fail_out);
+}
+// parts >= 3: the partitioned solver with that many fronts (BAGPU_ERR_ARG when the system is too short for them); otherwise one front.
+int bagpu_test_solve_parts(bagpu_ctx *ctx, int n, const int *col_end, const double *A, const double *b, double lambda, int parts, double *x, int *fail_out) {
     if (!ctx || n <= 0 || !col_end || !A || !b || !x) return BAGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     int band = 1, max_below = 0;
@@ -1550,6 +1772,25 @@ int bagpu_test_solve(bagpu_ctx *ctx, int n, const int *col_end, const double *A,
     CK(cudaMemcpyAsync(dc.p, col_end, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     int tgrid = 1, tmaxr = 0;
     { int rc2 = chol_plan_grid(ctx, n, max_below, &tgrid, &tmaxr); if (rc2) return rc2; }
+    if (parts >= 3) {
+        PartPlan pp;
+        std::vector<int> ce(col_end, col_end + n);
+        int rc2 = parts_plan(ctx, pp, n, ld, ce, parts, false, st);
+        if (rc2 == BAGPU_OK && !pp.on) rc2 = fail(ctx, BAGPU_ERR_ARG, "system of %d rows is too short (or its envelope too wide) for %d partitions", n, parts);
+        if (rc2 == BAGPU_OK) rc2 = parts_bind(ctx, pp, dS.as<double>(), db.as<double>(), dz.as<double>(), dy.as<double>(), dx.as<double>(), dd.as<double>(), df.as<int>(),
+                                             nullptr, nullptr, 0, nullptr, st);
+        if (rc2 == BAGPU_OK) rc2 = parts_enqueue_factor(ctx, pp, lambda, nullptr, st);
+        if (rc2 == BAGPU_OK) rc2 = parts_enqueue_rest(ctx, pp, dS.as<double>(), db.as<double>(), dz.as<double>(), dy.as<double>(), dx.as<double>(), lambda, df.as<int>(), st);
+        int hf = 0;
+        if (rc2 == BAGPU_OK) {
+            if (cudaMemcpyAsync(x, dx.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaMemcpyAsync(&hf, df.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) rc2 = fail(ctx, BAGPU_ERR_CUDA, "partitioned test solve: %s", cudaGetErrorString(cudaGetLastError()));
+        } else cudaStreamSynchronize(st);
+        if (fail_out) *fail_out = hf;
+        pp.release();
+        dS.release(); db.release(); dz.release(); dx.release(); dy.release(); dc.release(); df.release(); dd.release();
+        return rc2;
+    }
     CholArgs ca; ca.S = dS.as<double>(); ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = db.as<double>(); ca.bs = dz.as<double>();
     ca.col_end = dc.as<int>(); ca.y = dy.as<double>(); ca.dinv = dd.as<double>(); ca.prof = ctx->opt.debug ? (long long *)((char *)df.p + 16) : nullptr; ca.x = dx.as<double>(); ca.fail = df.as<int>();
     int rc = launch_chol(ctx, ca, tgrid, tmaxr);

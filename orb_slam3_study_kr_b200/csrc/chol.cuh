@@ -50,6 +50,10 @@ struct CholArgs {
     // original ordering: right-hand side, x, camera rows to wait for); back_from > 0: backward substitution only, for panels
     // back_from - 1 .. 0, with x of the rows >= 32 back_from already in y.
     int p_stop = 0, mirror_n = 0, back_from = 0, wait_band = 0;
+    // Partitioned factorisation (chol_parts.cuh): this system is the sub-system that starts at global row row_base (the camera
+    // rows to wait for are counted from there); no_back = 1: factor every panel and return (the backward substitution runs later,
+    // once the separator unknowns are known).
+    int row_base = 0, no_back = 0;
 };
 
 // One warp factors the 32x32 SPD block in shared memory (Ld[r][c], lower part), 8 columns at a time:
@@ -486,9 +490,16 @@ __device__ __forceinline__ void rank32_update(double *Cb, const double *Lr, cons
     }
 }
 
-__global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr, int dyn_doubles) {
+// table != nullptr: the grid holds one cluster per entry of `table` (the partitions of chol_parts.cuh, all with the same cluster
+// size and maxr); cluster q works on table[q] with the launch's lambda.
+__global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr, int dyn_doubles, const CholArgs *__restrict__ table) {
     cg::cluster_group cl = cg::this_cluster();
     const int NC = (int)cl.num_blocks(), o = (int)cl.block_rank();
+    if (table) {      // the launch carries lambda and whether to wait for pair_kernel's row counters; everything else is per partition
+        const double lam = a.lambda; const bool wait = a.row_done != nullptr;
+        a = table[blockIdx.x / NC]; a.lambda = lam;
+        if (!wait) a.row_done = nullptr;
+    }
     extern __shared__ double cb_sm[];
     double *Cb = cb_sm;                                        // own block column [maxr + pad][CB_LD]
     double *Ls = cb_sm + (size_t)(maxr + CB_PAD) * CB_LD;      // staged rows of the panel being applied
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
     auto load_block = [&](int c) {
         const int p0 = c * CH_NB, nb = min(CH_NB, n - p0);
         if (a.row_done) {                                  // wait for the camera rows of this block column (pair_kernel)
-            int a0 = p0 / 6, a1 = (p0 + nb - 1) / 6;
+            int a0 = (a.row_base + p0) / 6, a1 = (a.row_base + p0 + nb - 1) / 6;
             if (a.mirror_n) {                                  // mirrored system: original columns C_lo..C_hi, rows from C_lo - band up
                 const int c_hi = a.mirror_n - 1 - p0, c_lo = a.mirror_n - 1 - (p0 + nb - 1);
                 a0 = max(0, c_lo - a.wait_band) / 6; a1 = c_hi / 6;
@@ -769,7 +780,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, in
         }
         return;
     }
-    if (o != 0) return;
+    if (o != 0 || a.no_back) return;
     }   // a.back_from == 0
     else if (o != 0) return;
     BT(15);

@@ -1,0 +1,296 @@
+// Partitioned band Cholesky: P factorisation fronts instead of one or two (sm_100a).
+//
+// The chain of 32-column panels is the serial part of the reduced-camera-system solve (chol.cuh): 12 us per panel, so the
+// 5000-keyframe system of BASELINE config 5 (n = 29 994, 938 panels) costs 8.8 ms even when it is factored from both ends.
+// Here the band is cut into P interiors I_0 .. I_{P-1} with P-1 separators T_1 .. T_{P-1} between them, each at least as wide
+// as the band, so that no interior touches another one:
+//
+//        I_0 | T_1 | I_1 | T_2 | ... | T_{P-1} | I_{P-1}          (natural order, all boundaries multiples of 96 rows)
+//
+//  1. ONE launch of chol_band_kernel with a table of P sub-systems (one cluster each): cluster i factors I_i top-down and
+//     carries the updates into its BOTTOM separator T_{i+1} like into any trailing column (p_stop), exactly as the two-way
+//     solver does: T_{i+1} <- T_{i+1} - G_i G_i^T with G_i = L(T_{i+1}, I_i).
+//  2. The TOP separator T_i couples to the first rows of I_i. With the separators ordered last its row block of L is the
+//     "spike" V_i^T, V_i = L_i^{-1} A(I_i, T_i) (m_i x w, dense): spike_forward_kernel, a forward substitution with w right-hand
+//     sides. The columns are independent, so every CTA takes 8 of them and walks the panels alone (no barriers between CTAs);
+//     the 32x32 diagonal blocks are inverted beforehand (panel_inverse_kernel) so a panel step is two small products.
+//  3. spike_gram_kernel: the Schur complement the interior leaves on its separators,
+//         T_i <- T_i - V_i^T V_i,      E_i = -V_i^T G_i^T  (block T_i x T_{i+1}),      rhs(T_i) <- rhs(T_i) - V_i^T y_i.
+//  4. sep_assemble_kernel gathers the block-tridiagonal separator system ((P-1) w rows), the production solver factors it
+//     (one cluster / cooperative grid), sep_scatter_kernel puts x_T in place and spike_apply_kernel corrects the interiors'
+//     right-hand sides, y_i <- y_i - V_i x_{T_i}.
+//  5. ONE launch of chol_band_kernel (P single-CTA clusters, back_from) runs the P backward substitutions side by side.
+//
+// Every sum is formed in a fixed order (no atomics), so the solve stays bit-for-bit reproducible.
+// Replaces LinearSolverEigen::solve (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124) for long keyframe chains.
+#pragma once
+#include "chol.cuh"
+
+#define PS_MAX_PARTS 32
+#define PS_NCOL 8                 // right-hand sides per CTA of spike_forward_kernel
+#define PS_THREADS 256
+#define PS_WIN (CB_MAXR + 32)     // rows of the rolling window (a panel reaches at most CB_MAXR rows)
+
+struct PartDesc {
+    int r0;                       // first global row of the interior
+    int m;                        // interior rows
+    int k;                        // interior panels = ceil(m / 32)
+    int wT, wB;                   // rows of the top / bottom separator (0: none); the top one sits at [r0 - wT, r0)
+    int sep;                      // index of the top separator in the separator system (partition i >= 1: i - 1)
+    long long v_off;              // V_i (m x wT, row-major) in the spike buffer
+    long long linv_off;           // inverted diagonal blocks [k][32][32] (row-major, lower)
+    int ce_off;                   // col_end of the sub-system (relative rows) in the sub-system col_end array
+    int cta0;                     // first CTA of this partition in spike_forward_kernel's grid
+    int pan0;                     // first panel of this partition in panel_inverse_kernel's grid
+    int tile0;                    // first CTA of this partition in spike_gram_kernel's grid
+};
+struct PartTable { int P; int w; PartDesc d[PS_MAX_PARTS]; };
+
+// L^-1 of every 32x32 diagonal block of the interiors that carry a spike (partitions >= 1). warp = panel.
+// The band buffer holds L below the diagonal and 1 / L(j,j) on it (chol_band_kernel).
+#define PS_INV_WARPS 2
+__global__ void __launch_bounds__(32 * PS_INV_WARPS) panel_inverse_kernel(PartTable T, const double *__restrict__ S, int ld, double *__restrict__ linv, int n_panels) {
+    __shared__ double Ls[PS_INV_WARPS][32][33];
+    __shared__ double Xs[PS_INV_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gp = blockIdx.x * PS_INV_WARPS + warp;
+    if (gp >= n_panels) return;
+    int i = 1;
+    while (i + 1 < T.P && T.d[i + 1].pan0 <= gp) i++;
+    const PartDesc &D = T.d[i];
+    const int c = gp - D.pan0, p0 = 32 * c, nb = min(32, D.m - p0);
+    // Ls[r][j] = L(p0 + r, p0 + j) (lane = r)
+    for (int j = 0; j < 32; j++) {
+        double v = (lane == j) ? 1.0 : 0.0;
+        if (lane < nb && j < nb && j <= lane) v = __ldcg(S + (size_t)(D.r0 + p0 + j) * ld + D.r0 + p0 + lane);
+        Ls[warp][lane][j] = v;
+    }
+    __syncwarp();
+    // lane = column c of the inverse: x_i = (delta_ic - sum_{j<i} L_ij x_j) * (1 / L_ii)
+    for (int r = 0; r < 32; r++) {
+        double s = (r == lane) ? 1.0 : 0.0;
+        for (int j = lane; j < r; j++) s -= Ls[warp][r][j] * Xs[warp][j][lane];
+        Xs[warp][r][lane] = (r >= lane) ? s * Ls[warp][r][r] : 0.0;
+    }
+    __syncwarp();
+    double *out = linv + D.linv_off + (size_t)c * 1024;
+    for (int r = 0; r < 32; r++) out[r * 32 + lane] = Xs[warp][r][lane];
+}
+
+// V_i = L_i^-1 A(I_i, T_i) for PS_NCOL columns of T_i per CTA.
+__global__ void __launch_bounds__(PS_THREADS) spike_forward_kernel(PartTable T, const double *__restrict__ S, int ld, const int *__restrict__ sub_colend,
+                                                                   const double *__restrict__ linv, double *__restrict__ V) {
+    __shared__ double win[PS_WIN][PS_NCOL];          // rows p0 .. p0 + PS_WIN - 1 of the right-hand sides, circular in the row index
+    __shared__ double Li[32][33];
+    __shared__ double vp[32][PS_NCOL];
+    int i = 1;
+    while (i + 1 < T.P && T.d[i + 1].cta0 <= (int)blockIdx.x) i++;
+    const PartDesc &D = T.d[i];
+    const int t0 = ((int)blockIdx.x - D.cta0) * PS_NCOL;
+    const int tid = threadIdx.x;
+    const int *ce = sub_colend + D.ce_off;
+    const int rT = D.r0 - D.wT;                       // first global row of the top separator
+    // A(I, T)(r, t) = S[(rT + t) * ld + r0 + r] while the column stays inside the stored band of that row
+    for (int e = tid; e < PS_WIN * PS_NCOL; e += PS_THREADS) {
+        const int r = e / PS_NCOL, j = e - r * PS_NCOL, t = t0 + j;
+        double v = 0.0;
+        if (r < D.m && t < D.wT && (D.r0 + r) - (rT + t) <= ld) v = __ldcg(S + (size_t)(rT + t) * ld + D.r0 + r);
+        win[r][j] = v;
+    }
+    double *Vp = V + D.v_off;
+    for (int c = 0; c < D.k; c++) {
+        const int p0 = 32 * c, nb = min(32, D.m - p0);
+        const double *lp = linv + D.linv_off + (size_t)c * 1024;
+        for (int e = tid; e < 1024; e += PS_THREADS) Li[e >> 5][e & 31] = __ldcg(lp + e);
+        __syncthreads();
+        {   // v_p = L_pp^-1 win[p0 .. p0 + 31]
+            const int r = tid >> 3, j = tid & 7;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 32; q += 2) {
+                s0 += Li[r][q] * win[(p0 + q) % PS_WIN][j];
+                s1 += Li[r][q + 1] * win[(p0 + q + 1) % PS_WIN][j];
+            }
+            const double v = (r < nb) ? s0 + s1 : 0.0;
+            vp[r][j] = v;
+            if (r < nb && t0 + j < D.wT) Vp[(size_t)(p0 + r) * D.wT + t0 + j] = v;
+        }
+        __syncthreads();
+        // rows below the panel inside the interior: win[row] -= L(row, p0 .. p0 + 31) v_p
+        const int rend = min(D.m - 1, ce[p0 + nb - 1]);
+        for (int row = p0 + 32 + tid; row <= rend; row += PS_THREADS) {
+            double acc[PS_NCOL];
+            const int slot = row % PS_WIN;
+#pragma unroll
+            for (int j = 0; j < PS_NCOL; j++) acc[j] = win[slot][j];
+            const double *lrow = S + (size_t)(D.r0 + p0) * ld + D.r0 + row;
+#pragma unroll 8
+            for (int q = 0; q < 32; q++) {
+                const double l = (q < nb) ? __ldcg(lrow + (size_t)q * ld) : 0.0;
+#pragma unroll
+                for (int j = 0; j < PS_NCOL; j++) acc[j] -= l * vp[q][j];
+            }
+#pragma unroll
+            for (int j = 0; j < PS_NCOL; j++) win[slot][j] = acc[j];
+        }
+        // the 32 slots of this panel become rows p0 + PS_WIN ..: beyond the reach of A(I, T) (PS_WIN > band), so they start at zero
+        if (tid < 32 * PS_NCOL) win[(p0 + (tid >> 3)) % PS_WIN][tid & 7] = 0.0;
+        __syncthreads();
+    }
+}
+
+// Per partition i >= 1:  Dp_i = V_i^T V_i (upper 32x32 tiles),  Ep_i = V_i^T G_i^T (all tiles; G_i = L(T_{i+1}, I_i), only the last
+// rows of the interior reach it),  gp_i = V_i^T y_i.  CTA = one output tile, the whole sum in a fixed order.
+__global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const double *__restrict__ S, int ld, const double *__restrict__ V,
+                                                         const double *__restrict__ y, double *__restrict__ Dp, double *__restrict__ Ep, double *__restrict__ gp) {
+    __shared__ double As[32][33], Bs[32][33];
+    int i = 1;
+    while (i + 1 < T.P && T.d[i + 1].tile0 <= (int)blockIdx.x) i++;
+    const PartDesc &D = T.d[i];
+    const int w = D.wT, nt = w / 32, ntri = nt * (nt + 1) / 2;
+    int tile = (int)blockIdx.x - D.tile0;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double *Vp = V + D.v_off;
+    const size_t so = (size_t)D.sep * w * w;
+    if (tile < ntri) {                                   // ---- Dp: tile (a, b), a <= b
+        int a = 0;
+        while (tile >= nt - a) { tile -= nt - a; a++; }
+        const int b = a + tile;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int r0 = 0; r0 < D.m; r0 += 32) {
+            __syncthreads();
+            for (int e = tid; e < 1024; e += 256) {
+                const int rr = e >> 5, cc = e & 31;
+                const bool in = r0 + rr < D.m;
+                As[rr][cc] = in ? __ldcg(Vp + (size_t)(r0 + rr) * w + 32 * a + cc) : 0.0;
+                Bs[rr][cc] = in ? __ldcg(Vp + (size_t)(r0 + rr) * w + 32 * b + cc) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int rr = 0; rr < 32; rr++) {
+                const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
+                acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int v = 0; v < 2; v++) Dp[so + (size_t)(32 * a + ty + 16 * u) * w + 32 * b + tx + 16 * v] = acc[u][v];
+        return;
+    }
+    tile -= ntri;
+    if (tile < nt * nt && D.wB > 0) {                    // ---- Ep: tile (a, b) of V^T G^T, G(t, c) = L(m + t, c) = S[(r0 + c) * ld + r0 + m + t]
+        const int a = tile / nt, b = tile - a * nt;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        // interior columns c that reach separator row m + 32 b (and beyond): c >= m + 32 b - ld
+        const int cfirst = max(0, (D.m + 32 * b - ld) & ~31);
+        for (int r0 = cfirst; r0 < D.m; r0 += 32) {
+            __syncthreads();
+            for (int e = tid; e < 1024; e += 256) {
+                const int rr = e >> 5, cc = e & 31;
+                const int c = r0 + rr, trow = D.m + 32 * b + cc;                 // Bs[rr][cc] = G(32 b + cc, c)
+                const bool in = c < D.m;
+                As[rr][cc] = in ? __ldcg(Vp + (size_t)c * w + 32 * a + cc) : 0.0;
+                Bs[rr][cc] = (in && trow - c <= ld) ? __ldcg(S + (size_t)(D.r0 + c) * ld + D.r0 + trow) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int rr = 0; rr < 32; rr++) {
+                const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
+                acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int v = 0; v < 2; v++) Ep[so + (size_t)(32 * a + ty + 16 * u) * w + 32 * b + tx + 16 * v] = acc[u][v];
+        return;
+    }
+    if (tile == nt * nt) {                               // ---- gp = V^T y (thread = column, fixed order over the rows)
+        const double *yi = y + D.r0;
+        for (int t = tid; t < w; t += 256) {
+            double s0 = 0.0, s1 = 0.0;
+            int r = 0;
+            for (; r + 1 < D.m; r += 2) { s0 += __ldcg(Vp + (size_t)r * w + t) * __ldcg(yi + r); s1 += __ldcg(Vp + (size_t)(r + 1) * w + t) * __ldcg(yi + r + 1); }
+            if (r < D.m) s0 += __ldcg(Vp + (size_t)r * w + t) * __ldcg(yi + r);
+            gp[(size_t)D.sep * w + t] = s0 + s1;
+        }
+    }
+}
+
+// The separator system in band storage (element (R, C), R <= C, at SM[R * ldM + C]; lambda is added by the solver):
+//   diagonal block j:   S(T_j, T_j) as partition j-1... left it (A - G G^T, no lambda)  -  Dp_j
+//   block (j, j + 1):   -Ep_{j}'s partition: the interior between T_j and T_{j+1} couples them
+//   rhs:                b_p + b_s + y (the forward updates of the interior above)  -  gp_j
+// Separator j (0-based) sits at global rows sep_row[j] .. sep_row[j] + w - 1 and is the TOP separator of partition j + 1.
+__global__ void sep_assemble_kernel(int nsep, int w, const int *__restrict__ sep_row, const double *__restrict__ S, int ld, const double *__restrict__ bp,
+                                    const double *__restrict__ bs, const double *__restrict__ y, const double *__restrict__ Dp, const double *__restrict__ Ep,
+                                    const double *__restrict__ gp, double *__restrict__ SM, int ldM, double *__restrict__ rhsM) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)w * 2 * w;            // per separator row block: w rows x (own block + next block) columns
+    if (idx >= (long long)nsep * per) return;
+    const int j = (int)(idx / per);
+    const int rem = (int)(idx - (long long)j * per);
+    const int tr = rem / (2 * w), tc2 = rem - tr * 2 * w;
+    const int R = j * w + tr;
+    if (tc2 < w) {
+        const int tc = tc2;
+        if (tc < tr) return;
+        const int gr = sep_row[j] + tr, gc = sep_row[j] + tc;
+        double v = (gc - gr <= ld) ? S[(size_t)gr * ld + gc] : 0.0;
+        v -= Dp[(size_t)j * w * w + (size_t)tr * w + tc];
+        SM[(size_t)R * ldM + (j * w + tc)] = v;
+        if (tc == tr) rhsM[R] = bp[gr] + bs[gr] + y[gr] - gp[(size_t)j * w + tr];
+    } else if (j + 1 < nsep) {
+        const int tc = tc2 - w;
+        SM[(size_t)R * ldM + ((j + 1) * w + tc)] = -Ep[(size_t)j * w * w + (size_t)tr * w + tc];
+    }
+}
+
+// x_T into the final x and into y (the backward substitutions read the separator below their interior from y)
+__global__ void sep_scatter_kernel(int nsep, int w, const int *__restrict__ sep_row, const double *__restrict__ xM, double *__restrict__ y, double *__restrict__ x) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nsep * w) return;
+    const int j = idx / w, t = idx - j * w;
+    const double v = xM[idx];
+    y[sep_row[j] + t] = v; x[sep_row[j] + t] = v;
+}
+
+// y_i <- y_i - V_i x_{T_i} for the interiors with a top separator. warp = row.
+__global__ void __launch_bounds__(256) spike_apply_kernel(PartTable T, const double *__restrict__ V, const double *__restrict__ xM, double *__restrict__ y, int rows_total) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= rows_total) return;
+    int i = 1, base = 0;
+    while (i + 1 < T.P && base + T.d[i].m <= g) { base += T.d[i].m; i++; }
+    const PartDesc &D = T.d[i];
+    const int r = g - base;
+    if (r >= D.m) return;
+    const double *vr = V + D.v_off + (size_t)r * D.wT;
+    const double *xt = xM + (size_t)D.sep * D.wT;
+    double s = 0.0;
+    for (int t = lane; t < D.wT; t += 32) s += __ldcg(vr + t) * __ldcg(xt + t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[D.r0 + r] -= s;
+}
+
+// order in which pair_kernel takes the camera rows when the factorisation has P fronts: round-robin over the sub-systems
+// (interior + bottom separator), each from its first camera down, so that every cluster is fed from the start.
+__global__ void row_order_parts_kernel(int nf, PartTable T, int *row_pos, int *row_of_pos) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nf) return;
+    // sub-system q owns the cameras of its interior and of its bottom separator: [r0_q / 6, r0_{q+1} / 6)
+    int owner = 0;
+    while (owner + 1 < T.P && T.d[owner + 1].r0 / 6 <= a) owner++;
+    const int first = (owner == 0) ? 0 : T.d[owner].r0 / 6;
+    const int t = a - first;
+    int pos = 0;
+    for (int q = 0; q < T.P; q++) {
+        const int f = (q == 0) ? 0 : T.d[q].r0 / 6;
+        const int e = (q + 1 < T.P) ? T.d[q + 1].r0 / 6 : nf;                         // one past the last camera of sub-system q (interior + bottom separator)
+        const int len = e - f;
+        pos += min(t, len) + ((q < owner && len > t) ? 1 : 0);
+    }
+    row_pos[a] = pos; row_of_pos[pos] = a;
+}

@@ -224,3 +224,32 @@ def test_solver_variants_agree():
             assert abs(a - b) <= 1e-9 * abs(b), (extra, a, b)
         assert abs(got["pose_sum"] - base["pose_sum"]) <= 1e-9 * base["pose_sum"], extra
         assert abs(got["point_sum"] - base["point_sum"]) <= 1e-9 * base["point_sum"], extra
+
+
+def test_partitioned_solver_in_the_lm_loop():
+    """Config 4 at 1/2 size (250 keyframes, n = 1494) and at full size with the partitioned solver forced (BAGPU_PARTS): the LM
+    trajectory equals the default solver's, beside pair_kernel (row counters per sub-system) and after it."""
+    import json
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_worker.py")
+
+    def run(extra):
+        env = dict(os.environ)
+        env.update(extra)
+        out = subprocess.run([sys.executable, worker], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    for scale, variants in (("0.5", ({"BAGPU_PARTS": "3"}, {"BAGPU_PARTS": "3", "BAGPU_NO_OVERLAP": "1"})),
+                            ("1.0", ({"BAGPU_PARTS": "4"}, {"BAGPU_PARTS": "5", "BAGPU_NO_OVERLAP": "1"}))):
+        base = run({"VARIANT_SCALE": scale})
+        assert base["solver_parts"] == 2
+        for extra in variants:
+            got = run(dict(extra, VARIANT_SCALE=scale))
+            assert got["solver_parts"] == int(extra["BAGPU_PARTS"]), (extra, got["solver_parts"])
+            assert got["trials"] == base["trials"], (extra, got["trials"], base["trials"])
+            for a, b in zip(got["chi2"], base["chi2"]):
+                assert abs(a - b) <= 1e-9 * abs(b), (extra, a, b)
+            assert abs(got["pose_sum"] - base["pose_sum"]) <= 1e-9 * base["pose_sum"], extra
+            assert abs(got["point_sum"] - base["point_sum"]) <= 1e-9 * base["point_sum"], extra

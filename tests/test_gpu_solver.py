@@ -66,3 +66,48 @@ def test_solver_flags_indefinite(ctx):
     # and the context keeps working afterwards
     x, fail = ctx.test_solve(np.eye(n) * 2.0, np.ones(n), np.minimum(n - 1, np.arange(n) + 20).astype(np.int32), 0.0)
     assert not fail and np.allclose(x, 0.5)
+
+
+# ---------------------------------------------------------------- partitioned solver (chol_parts.cuh): P fronts, spikes, separator system
+@pytest.mark.parametrize("n,bw,parts", [(1500, 60, 3), (2000, 100, 4), (3000, 180, 4), (2994, 185, 3), (4000, 90, 8), (6000, 185, 6), (2500, 30, 5)])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_partitioned_solver_matches_numpy(ctx, n, bw, parts, ragged):
+    """(A + lambda I) x = b through P factorisation fronts + spikes + the block-tridiagonal separator system, against numpy and
+    against the one-front solver; n not a multiple of 32 or 96, ragged envelopes, up to 8 fronts."""
+    rng = np.random.default_rng(n + 7 * bw + parts + int(ragged))
+    A, ce = _banded_spd(n, bw, rng, ragged)
+    b = rng.normal(size=n)
+    x, fail = ctx.test_solve(A, b, ce, 0.5, parts=parts)
+    assert not fail
+    ref = np.linalg.solve(A + 0.5 * np.eye(n), b)
+    assert np.abs(x - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    x1, _ = ctx.test_solve(A, b, ce, 0.5)
+    assert np.abs(x - x1).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    # bit-for-bit reproducible: no atomics anywhere in the partitioned path
+    x2, _ = ctx.test_solve(A, b, ce, 0.5, parts=parts)
+    assert np.array_equal(x, x2)
+
+
+def test_partitioned_solver_ill_conditioned_and_failure(ctx):
+    """Badly scaled Gram matrix (condition ~1e8) through 4 fronts; an indefinite interior raises the failure flag like the
+    one-front solver; a system too short for the requested fronts is refused with an error, not solved wrongly."""
+    from orb_slam3_study_kr_b200 import api
+    rng = np.random.default_rng(5)
+    n, h, env = 2994, 90, 185
+    Bb = np.zeros((n, n + h))
+    for i in range(n):
+        Bb[i, i:i + h + 1] = rng.normal(size=h + 1)
+    A = Bb @ Bb.T
+    sc = 10.0 ** rng.uniform(-3, 3, size=n)
+    A = A * sc[:, None] * sc[None, :]
+    ce = np.minimum(n - 1, np.arange(n) + env).astype(np.int32)
+    b = rng.normal(size=n)
+    lam = 1e-8 * np.abs(np.diag(A)).max()
+    ref = np.linalg.solve(A + lam * np.eye(n), b)
+    x, fail = ctx.test_solve(A, b, ce, lam, parts=4)
+    assert not fail and np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+    A2 = A.copy(); A2[1700, 1700] = -abs(A2[1700, 1700])
+    _, fail = ctx.test_solve(A2, b, ce, lam, parts=4)
+    assert fail
+    with pytest.raises(api.BagpuError):
+        ctx.test_solve(A[:600, :600], b[:600], np.minimum(599, ce[:600]), lam, parts=4)

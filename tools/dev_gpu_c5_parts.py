@@ -1,0 +1,31 @@
+"""Development script (not a test): full config 5 on one GPU with different numbers of factorisation fronts (BAGPU_PARTS)."""
+import os, sys, time
+sys.path.insert(0, ".")
+from orb_slam3_study_kr_b200 import api, synthetic, problem
+
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+p = synthetic.config(cfg, robust=False)
+print(f"poses {p.n_poses} points {p.n_points} obs {p.n_obs}", flush=True)
+s = problem.schedule_global_ba(20)
+base = None
+for parts, extra in [("2", {}), ("4", {}), ("6", {}), ("8", {}), ("12", {}), ("16", {}), ("2", {"BAGPU_NO_OVERLAP": "1"}), ("4", {"BAGPU_NO_OVERLAP": "1"}),
+                     ("8", {"BAGPU_NO_OVERLAP": "1"}), ("12", {"BAGPU_NO_OVERLAP": "1"}), ("16", {"BAGPU_NO_OVERLAP": "1"}), ("24", {"BAGPU_NO_OVERLAP": "1"})]:
+    os.environ["BAGPU_PARTS"] = parts
+    for k in ("BAGPU_NO_OVERLAP",):
+        os.environ.pop(k, None)
+    os.environ.update(extra)
+    ctx = api.Context(0)
+    ctx.upload(p)
+    got = ctx.solve_resident(s)
+    ctx.reset_resident()
+    t1 = time.time()
+    got = ctx.solve_resident(s)
+    tm = ctx.timing()
+    chis = [t["chi2_after"] for t in got.trace]
+    if base is None:
+        base = chis
+    dev = max(abs(a - b) / b for a, b in zip(chis, base)) if len(chis) == len(base) else -1
+    print(f"parts {parts:>2} {extra}: solver_parts {tm['solver_parts']} solve_ms {tm['solve_ms']:.1f} trials {tm['lm_trials']} per-trial {tm['solve_ms'] / tm['lm_trials']:.2f} ms | "
+          f"build {tm['build_ms'] / tm['build_launches']:.2f} linsolve {tm['linsolve_ms'] / max(1, tm['linsolve_launches']):.2f} update {tm['update_ms'] / tm['update_launches']:.2f} | "
+          f"max rel chi2 dev vs first {dev:.2e} retries {tm['solve_retries']}", flush=True)
+    ctx.close()
