@@ -1070,16 +1070,19 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
         while (P >= 3 && interior_of(P) < std::max(w, 192)) P--;
         if (P < 3) return BAGPU_OK;
     } else {
-        // cost model (us; measured on B200: ~19 us per 32-column panel of the chain on long systems, ~20 us per separator panel in
-        // the tiled solver, ~0.3 ms of extra launches): fronts pay off from roughly 1000 keyframes on
-        const double panels = n / 32.0, two_way = panels / 2 * 19.0 + 250.0;
-        double best = 0.75 * two_way;
-        // beside pair_kernel the clusters take SMs away from it: stay within a quarter of the device there
-        const int p_cap = overlap_possible ? std::max(3, ctx->n_sm / 4 / 8) : PS_MAX_PARTS;
-        for (int q = 3; q <= std::min(PS_MAX_PARTS, p_cap); q++) {
+        // Beside pair_kernel (one GPU) the two-front solver wins: its chain nearly keeps pace with the accumulation, while P spinning
+        // clusters take SMs away from pair_kernel and leave a longer tail (spikes + separator system) after it -- measured on config 5:
+        // 13.5 ms per trial with two fronts, 16.0 / 17.7 ms with 4 / 8. The fronts pay off where the solve is exposed: after the
+        // all-reduce of a multi-GPU trial, or when the overlap is off.
+        if (overlap_possible) return BAGPU_OK;
+        // cost model (us; measured on B200, config 5: ~19 us per 32-column panel of the chain, ~40 us per panel of the separator system in
+        // the tiled solver, ~0.6 ms for the spikes, their products and the extra launches; the two-front solver runs at ~16 us per panel)
+        const double panels = n / 32.0, two_way = panels / 2 * 16.0 + 250.0;
+        double best = 0.8 * two_way;
+        for (int q = 3; q <= PS_MAX_PARTS; q++) {
             const int per = interior_of(q);
             if (per < std::max(2 * w, 576)) break;
-            const double c = (per / 32.0 + w / 32.0) * 19.0 + (q - 1) * (w / 32.0) * 20.0 + 300.0;
+            const double c = (per / 32.0 + w / 32.0) * 19.0 + (q - 1) * (w / 32.0) * 40.0 + 600.0;
             if (c < best) { best = c; P = q; }
         }
         if (P < 3) return BAGPU_OK;
