@@ -118,6 +118,7 @@ struct BagpuOptions {
     bool no_cluster = false;     // BAGPU_NO_CLUSTER: cooperative launch instead of one cluster for chol_solve_kernel
     bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
     int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
+    bool sep_tiled = false;      // BAGPU_SEP_TILED: separator system through the tiled band solver instead of block cyclic reduction
     void read() {
         auto on = [](const char *k) { return getenv(k) != nullptr; };
         debug = on("BAGPU_DEBUG"); no_twoway = on("BAGPU_NO_TWOWAY"); compare = on("BAGPU_COMPARE"); no_tiles = on("BAGPU_NO_TILES");
@@ -127,6 +128,7 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
+        sep_tiled = on("BAGPU_SEP_TILED");
     }
 };
 
@@ -141,8 +143,15 @@ struct PartPlan {
     std::vector<int> h_subce, h_seprow, h_ceM;           // kept alive: copied without a sync
     std::vector<CholArgs> h_tab;                         // [0, P): factorisation, [P, 2P): backward substitution
     DevBuf d_tab, d_subce, d_seprow, d_V, d_linv, d_Dp, d_Ep, d_gp, d_SM, d_rhsM, d_zeroM, d_yM, d_xM, d_ceM, d_dinvM;
+    // separator system by block cyclic reduction: dense blocks, per-level launch lists
+    bool cr = false; int cr_nc = 1;
+    CrPlan C;
+    std::vector<int> cr_stride, cr_cnt, cr_off, h_cedense;     // per level: stride s, eliminated blocks, offset into the tables
+    std::vector<CholArgs> h_crtab;                             // [0, K): factorisation in level order, [K, 2K): backward substitution
+    DevBuf d_crtab, d_Dd, d_Cc, d_gg, d_yy, d_Fa, d_Fb, d_linvB, d_cedense;
     void release() {
-        DevBuf *b[] = {&d_tab, &d_subce, &d_seprow, &d_V, &d_linv, &d_Dp, &d_Ep, &d_gp, &d_SM, &d_rhsM, &d_zeroM, &d_yM, &d_xM, &d_ceM, &d_dinvM};
+        DevBuf *b[] = {&d_tab, &d_subce, &d_seprow, &d_V, &d_linv, &d_Dp, &d_Ep, &d_gp, &d_SM, &d_rhsM, &d_zeroM, &d_yM, &d_xM, &d_ceM, &d_dinvM,
+                       &d_crtab, &d_Dd, &d_Cc, &d_gg, &d_yy, &d_Fa, &d_Fb, &d_linvB, &d_cedense};
         for (DevBuf *x : b) x->release();
     }
 };
@@ -458,7 +467,8 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
                              (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel,
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
-                             (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel};
+                             (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
+                             (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
         // so a second context on another GPU of the same process gets its large dynamic shared memory and cluster sizes too.
@@ -1143,9 +1153,34 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
     CK(cudaMemsetAsync(pp.d_zeroM.p, 0, 8 * nS, st));
     CK(cudaMemsetAsync(pp.d_SM.p, 0, 8 * (nS * (pp.ldM + 1) + 8), st));
     CK(cudaMemsetAsync(pp.d_Ep.p, 0, 8 * ww, st));
+    // separator system: block cyclic reduction over the K = P - 1 dense blocks (levels of independent eliminations)
+    pp.cr = !ctx->opt.sep_tiled && w <= CR_MAXW && w <= CB_MAXR;
+    if (pp.cr) {
+        const int K = P - 1;
+        pp.cr_stride.clear(); pp.cr_cnt.clear(); pp.cr_off.clear();
+        int off = 0;
+        for (int sft = 1; sft - 1 < K; sft *= 2) {
+            const int cnt = (K - (sft - 1) + 2 * sft - 1) / (2 * sft);
+            if (cnt <= 0) break;
+            pp.cr_stride.push_back(sft); pp.cr_cnt.push_back(cnt); pp.cr_off.push_back(off);
+            off += cnt;
+        }
+        pp.cr_nc = 2;
+        while (pp.cr_nc * CH_NB < w) pp.cr_nc *= 2;
+        pp.h_cedense.assign(w, w - 1);
+        const size_t kw = (size_t)K * w;
+        CK(pp.d_Dd.ensure(8 * ww)); CK(pp.d_Cc.ensure(8 * ww)); CK(pp.d_Fa.ensure(8 * ww)); CK(pp.d_Fb.ensure(8 * ww));
+        CK(pp.d_gg.ensure(8 * kw)); CK(pp.d_yy.ensure(8 * kw)); CK(pp.d_linvB.ensure(8 * (size_t)K * (w / 32) * 1024));
+        CK(pp.d_cedense.ensure(4 * (size_t)w)); CK(pp.d_crtab.ensure(sizeof(CholArgs) * 2 * (size_t)K));
+        CK(cudaMemcpyAsync(pp.d_cedense.p, pp.h_cedense.data(), 4 * (size_t)w, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(pp.d_Dd.p, 0, 8 * ww, st)); CK(cudaMemsetAsync(pp.d_Cc.p, 0, 8 * ww, st));
+        pp.C.K = K; pp.C.w = w; pp.C.Dd = pp.d_Dd.as<double>(); pp.C.Cc = pp.d_Cc.as<double>(); pp.C.gg = pp.d_gg.as<double>(); pp.C.yy = pp.d_yy.as<double>();
+        pp.C.xx = pp.d_xM.as<double>(); pp.C.Fa = pp.d_Fa.as<double>(); pp.C.Fb = pp.d_Fb.as<double>(); pp.C.linv = pp.d_linvB.as<double>();
+    }
     pp.on = true;
     if (ctx->opt.debug) fprintf(stderr, "[bagpu] partitioned solver: P=%d w=%d interior=%d (last %d) nc=%d maxr=%d | separator system n=%d ld=%d grid=%d maxr=%d | V %.1f MB\n",
                                 P, w, per, T.d[P - 1].m, nc, maxr, pp.nS, pp.ldM, pp.gridM, pp.maxrM, 8.0 * v_off / 1e6);
+    if (ctx->opt.debug && pp.cr) fprintf(stderr, "[bagpu] separator system by block cyclic reduction: %d blocks of %d rows, %zu levels\n", P - 1, w, pp.cr_stride.size());
     return BAGPU_OK;
 }
 
@@ -1168,24 +1203,41 @@ int parts_bind(bagpu_ctx *ctx, PartPlan &pp, double *S, double *bp, double *bs, 
         pp.h_tab[P + i] = b;
     }
     CK(cudaMemcpyAsync(pp.d_tab.p, pp.h_tab.data(), sizeof(CholArgs) * 2 * (size_t)P, cudaMemcpyHostToDevice, st));
+    if (pp.cr) {
+        const int K = pp.C.K, w = pp.C.w;
+        pp.h_crtab.assign(2 * (size_t)K, CholArgs());
+        int pos = 0;
+        for (size_t lv = 0; lv < pp.cr_stride.size(); lv++)
+            for (int t = 0; t < pp.cr_cnt[lv]; t++, pos++) {
+                const int j = pp.cr_stride[lv] - 1 + 2 * pp.cr_stride[lv] * t;
+                CholArgs a;
+                a.S = pp.C.Dd + (size_t)j * w * w; a.n = w; a.ld = w; a.lambda = 0.0; a.bp = pp.C.gg + (size_t)j * w; a.bs = pp.d_zeroM.as<double>();
+                a.col_end = pp.d_cedense.as<int>(); a.y = pp.C.yy + (size_t)j * w; a.dinv = pp.d_dinvM.as<double>() + (size_t)j * w; a.x = pp.C.xx + (size_t)j * w;
+                a.fail = failp; a.prof = nullptr; a.no_back = 1;
+                pp.h_crtab[pos] = a;
+                CholArgs b = a; b.no_back = 0; b.back_from = w / CH_NB;
+                pp.h_crtab[K + pos] = b;
+            }
+        CK(cudaMemcpyAsync(pp.d_crtab.p, pp.h_crtab.data(), sizeof(CholArgs) * 2 * (size_t)K, cudaMemcpyHostToDevice, st));
+    }
     return BAGPU_OK;
 }
 
-int parts_launch_table(bagpu_ctx *ctx, const PartPlan &pp, const CholArgs *table, int cluster, double lambda, const unsigned *wait, cudaStream_t stream) {
+int parts_launch_table(bagpu_ctx *ctx, const CholArgs *table, int count, int cluster, int maxr, int n_max, double lambda, const unsigned *wait, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(pp.P * cluster); cfg.blockDim = dim3(CB_THREADS); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.dynamicSmemBytes = chol_band_smem(ctx, pp.n_max, pp.maxr);
+    cfg.gridDim = dim3(count * cluster); cfg.blockDim = dim3(CB_THREADS); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = chol_band_smem(ctx, n_max, maxr);
     CholArgs a; a.lambda = lambda; a.row_done = wait; a.S = nullptr; a.n = 0; a.ld = 0; a.bp = a.bs = nullptr; a.col_end = nullptr;
     a.y = a.dinv = a.x = nullptr; a.fail = nullptr; a.prof = nullptr;
-    CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, pp.maxr, (int)(cfg.dynamicSmemBytes / sizeof(double)), table));
+    CK(cudaLaunchKernelEx(&cfg, chol_band_kernel, a, maxr, (int)(cfg.dynamicSmemBytes / sizeof(double)), table));
     return BAGPU_OK;
 }
 // the P factorisation fronts (one launch); wait != nullptr: the clusters consume camera rows as pair_kernel completes them
 int parts_enqueue_factor(bagpu_ctx *ctx, const PartPlan &pp, double lambda, const unsigned *wait, cudaStream_t stream) {
-    return parts_launch_table(ctx, pp, pp.d_tab.as<CholArgs>(), pp.nc, lambda, wait, stream);
+    return parts_launch_table(ctx, pp.d_tab.as<CholArgs>(), pp.P, pp.nc, pp.maxr, pp.n_max, lambda, wait, stream);
 }
 // spikes, separator system, backward substitutions
 int parts_enqueue_rest(bagpu_ctx *ctx, PartPlan &pp, const double *S, const double *bp, const double *bs, double *y, double *x, double lambda, int *failp, cudaStream_t st) {
@@ -1195,16 +1247,39 @@ int parts_enqueue_rest(bagpu_ctx *ctx, PartPlan &pp, const double *S, const doub
     spike_forward_kernel<<<pp.spike_ctas, PS_THREADS, 0, st>>>(T, S, pp.ld, pp.d_subce.as<int>(), pp.d_linv.as<double>(), pp.d_V.as<double>());
     spike_gram_kernel<<<pp.gram_ctas, 256, 0, st>>>(T, S, pp.ld, pp.d_V.as<double>(), y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(), pp.d_gp.as<double>());
     const long long na = (long long)nsep * w * 2 * w;
+    if (pp.cr) {
+        const CrPlan &C = pp.C;
+        const int K = C.K, np = w / 32, nt = w / 32;
+        cr_assemble_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(C, pp.d_seprow.as<int>(), S, pp.ld, bp, bs, y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(), pp.d_gp.as<double>());
+        CK(cudaMemsetAsync(pp.d_yy.p, 0, 8 * (size_t)K * w, st));
+        const size_t nl = pp.cr_stride.size();
+        for (size_t lv = 0; lv < nl; lv++) {
+            const int sft = pp.cr_stride[lv], cnt = pp.cr_cnt[lv];
+            { int rc = parts_launch_table(ctx, pp.d_crtab.as<CholArgs>() + pp.cr_off[lv], cnt, pp.cr_nc, w, w, lambda, nullptr, st); if (rc) return rc; }
+            const int n_keep = (K >= 2 * sft) ? (K - (2 * sft - 1) + 2 * sft - 1) / (2 * sft) : 0;
+            if (n_keep > 0) {
+                block_inverse_kernel<<<(cnt * np + PS_INV_WARPS - 1) / PS_INV_WARPS, 32 * PS_INV_WARPS, 0, st>>>(C, sft, cnt);
+                block_spike_kernel<<<cnt * 2 * (w / PS_NCOL), PS_THREADS, 0, st>>>(C, sft, cnt);
+                block_gram_kernel<<<n_keep * (2 * nt * nt + 1), 256, 0, st>>>(C, sft, n_keep);
+            }
+        }
+        for (size_t lv = nl; lv-- > 0;) {
+            const int sft = pp.cr_stride[lv], cnt = pp.cr_cnt[lv];
+            if (lv + 1 < nl) block_apply_kernel<<<(cnt * w + 7) / 8, 256, 0, st>>>(C, sft, cnt);
+            { int rc = parts_launch_table(ctx, pp.d_crtab.as<CholArgs>() + K + pp.cr_off[lv], cnt, 1, w, w, lambda, nullptr, st); if (rc) return rc; }
+        }
+    } else {
     sep_assemble_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(nsep, w, pp.d_seprow.as<int>(), S, pp.ld, bp, bs, y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(),
                                                                     pp.d_gp.as<double>(), pp.d_SM.as<double>(), pp.ldM, pp.d_rhsM.as<double>());
     CK(cudaMemsetAsync(pp.d_yM.p, 0, 8 * (size_t)pp.nS, st));
     CholArgs cM; cM.S = pp.d_SM.as<double>(); cM.n = pp.nS; cM.ld = pp.ldM; cM.lambda = lambda; cM.bp = pp.d_rhsM.as<double>(); cM.bs = pp.d_zeroM.as<double>();
     cM.col_end = pp.d_ceM.as<int>(); cM.y = pp.d_yM.as<double>(); cM.dinv = pp.d_dinvM.as<double>(); cM.x = pp.d_xM.as<double>(); cM.fail = failp; cM.prof = nullptr;
     { int rc = launch_chol(ctx, cM, pp.gridM, pp.maxrM, st); if (rc) return rc; }
+    }
     sep_scatter_kernel<<<(nsep * w + 255) / 256, 256, 0, st>>>(nsep, w, pp.d_seprow.as<int>(), pp.d_xM.as<double>(), y, x);
     spike_apply_kernel<<<(pp.apply_rows + 7) / 8, 256, 0, st>>>(T, pp.d_V.as<double>(), pp.d_xM.as<double>(), y, pp.apply_rows);
     CK(cudaGetLastError());
-    return parts_launch_table(ctx, pp, pp.d_tab.as<CholArgs>() + pp.P, 1, lambda, nullptr, st);
+    return parts_launch_table(ctx, pp.d_tab.as<CholArgs>() + pp.P, pp.P, 1, pp.maxr, pp.n_max, lambda, nullptr, st);
 }
 
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {

@@ -294,3 +294,201 @@ __global__ void row_order_parts_kernel(int nf, PartTable T, int *row_pos, int *r
     }
     row_pos[a] = pos; row_of_pos[pos] = a;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Separator system by block cyclic reduction.
+//
+// The separator system is block tridiagonal: K = P - 1 dense w x w diagonal blocks D_j, couplings C_j = block (j, j + 1), right-hand
+// sides g_j. Factoring it as one band system is again a serial chain (6 K panels, and with a reach of 2 w rows it does not fit the
+// shared-memory window of chol_band_kernel). Level l (stride s = 2^l) eliminates every second block that is still active
+// (j = s - 1 + 2 s t), all of them AT ONCE: their neighbours j - s and j + s are not eliminated at this level, so the blocks are
+// independent. Per level:
+//   factor       D_j + lambda I = L_j L_j^T, y_j = L_j^-1 g_j        chol_band_kernel, one cluster per block (table launch, no_back)
+//   spikes       Fa_j = L_j^-1 C_{j-s}^T,  Fb_j = L_j^-1 C_j         block_inverse_kernel + block_spike_kernel
+//   reduce       D_t -= Fb_{t-s}^T Fb_{t-s} + Fa_{t+s}^T Fa_{t+s},   g_t -= Fb_{t-s}^T y_{t-s} + Fa_{t+s}^T y_{t+s},
+//                C_t (now block (t, t + 2 s)) = -Fa_{t+s}^T Fb_{t+s}  for the blocks t that stay      block_gram_kernel
+// and on the way back, level by level:  y_j -= Fa_j x_{j-s} + Fb_j x_{j+s}  (block_apply_kernel),  x_j = L_j^-T y_j  (table launch).
+// log2(K) levels of one dense w x w factorisation each instead of K of them in a row; every sum in a fixed order.
+struct CrPlan { int K, w; double *Dd, *Cc, *gg, *yy, *xx, *Fa, *Fb, *linv; };
+
+// level-0 blocks from the band buffer and the interiors' products (same content as sep_assemble_kernel, dense block layout)
+__global__ void cr_assemble_kernel(CrPlan C, const int *__restrict__ sep_row, const double *__restrict__ S, int ld, const double *__restrict__ bp,
+                                   const double *__restrict__ bs, const double *__restrict__ y, const double *__restrict__ Dp, const double *__restrict__ Ep,
+                                   const double *__restrict__ gp) {
+    const int w = C.w;
+    const long long per = (long long)w * 2 * w;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)C.K * per) return;
+    const int j = (int)(idx / per);
+    const int rem = (int)(idx - (long long)j * per);
+    const int tr = rem / (2 * w), tc2 = rem - tr * 2 * w;
+    const size_t bo = (size_t)j * w * w;
+    if (tc2 < w) {
+        const int tc = tc2;
+        if (tc < tr) return;
+        const int gr = sep_row[j] + tr, gc = sep_row[j] + tc;
+        const double v = ((gc - gr <= ld) ? S[(size_t)gr * ld + gc] : 0.0) - Dp[bo + (size_t)tr * w + tc];
+        C.Dd[bo + (size_t)tr * w + tc] = v;
+        if (tc == tr) C.gg[(size_t)j * w + tr] = bp[gr] + bs[gr] + y[gr] - gp[(size_t)j * w + tr];
+    } else if (j + 1 < C.K) {
+        const int tc = tc2 - w;
+        C.Cc[bo + (size_t)tr * w + tc] = -Ep[bo + (size_t)tr * w + tc];
+    }
+}
+
+// inverse of the 32x32 diagonal blocks of the factored D_j of this level. warp = (block, panel)
+__global__ void __launch_bounds__(32 * PS_INV_WARPS) block_inverse_kernel(CrPlan C, int s, int cnt) {
+    __shared__ double Ls[PS_INV_WARPS][32][33];
+    __shared__ double Xs[PS_INV_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int np = C.w / 32;
+    const int g = blockIdx.x * PS_INV_WARPS + warp;
+    if (g >= cnt * np) return;
+    const int j = s - 1 + 2 * s * (g / np), c = g % np, p0 = 32 * c;
+    const double *L = C.Dd + (size_t)j * C.w * C.w;
+    for (int q = 0; q < 32; q++) Ls[warp][lane][q] = (q <= lane) ? __ldcg(L + (size_t)(p0 + q) * C.w + p0 + lane) : 0.0;
+    __syncwarp();
+    for (int r = 0; r < 32; r++) {
+        double sum = (r == lane) ? 1.0 : 0.0;
+        for (int q = lane; q < r; q++) sum -= Ls[warp][r][q] * Xs[warp][q][lane];
+        Xs[warp][r][lane] = (r >= lane) ? sum * Ls[warp][r][r] : 0.0;
+    }
+    __syncwarp();
+    double *out = C.linv + ((size_t)j * np + c) * 1024;
+    for (int r = 0; r < 32; r++) out[r * 32 + lane] = Xs[warp][r][lane];
+}
+
+// Fa_j = L_j^-1 C_{j-s}^T (side 0), Fb_j = L_j^-1 C_j (side 1), PS_NCOL columns per CTA; blockIdx = ((t * 2 + side) * (w / PS_NCOL) + group)
+#define CR_MAXW 384
+__global__ void __launch_bounds__(PS_THREADS) block_spike_kernel(CrPlan C, int s, int cnt) {
+    __shared__ double win[CR_MAXW][PS_NCOL];
+    __shared__ double Li[32][33];
+    __shared__ double vp[32][PS_NCOL];
+    const int w = C.w, ng = w / PS_NCOL, tid = threadIdx.x;
+    const int grp = blockIdx.x % ng, side = (blockIdx.x / ng) & 1, t = blockIdx.x / (2 * ng);
+    const int j = s - 1 + 2 * s * t;
+    if (side == 0 ? (j - s < 0) : (j + s >= C.K)) return;
+    const int t0 = grp * PS_NCOL;
+    const double *src = C.Cc + (size_t)(side == 0 ? j - s : j) * w * w;
+    for (int e = tid; e < w * PS_NCOL; e += PS_THREADS) {
+        const int r = e / PS_NCOL, q = e - r * PS_NCOL;
+        win[r][q] = (side == 0) ? __ldcg(src + (size_t)(t0 + q) * w + r) : __ldcg(src + (size_t)r * w + t0 + q);
+    }
+    const double *L = C.Dd + (size_t)j * w * w;
+    double *F = (side == 0 ? C.Fa : C.Fb) + (size_t)j * w * w;
+    const int np = w / 32;
+    for (int c = 0; c < np; c++) {
+        const int p0 = 32 * c;
+        const double *lp = C.linv + ((size_t)j * np + c) * 1024;
+        for (int e = tid; e < 1024; e += PS_THREADS) Li[e >> 5][e & 31] = __ldcg(lp + e);
+        __syncthreads();
+        {
+            const int r = tid >> 3, q = tid & 7;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < 32; k += 2) { s0 += Li[r][k] * win[p0 + k][q]; s1 += Li[r][k + 1] * win[p0 + k + 1][q]; }
+            vp[r][q] = s0 + s1;
+            F[(size_t)(p0 + r) * w + t0 + q] = s0 + s1;
+        }
+        __syncthreads();
+        for (int row = p0 + 32 + tid; row < w; row += PS_THREADS) {
+            double acc[PS_NCOL];
+#pragma unroll
+            for (int q = 0; q < PS_NCOL; q++) acc[q] = win[row][q];
+            const double *lrow = L + (size_t)p0 * w + row;
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const double l = __ldcg(lrow + (size_t)k * w);
+#pragma unroll
+                for (int q = 0; q < PS_NCOL; q++) acc[q] -= l * vp[k][q];
+            }
+#pragma unroll
+            for (int q = 0; q < PS_NCOL; q++) win[row][q] = acc[q];
+        }
+        __syncthreads();
+    }
+}
+
+// out (32x32 tile (a, b)) = X^T Y over the w rows, X and Y row-major w x w. 256 threads, 2x2 outputs each.
+__device__ __forceinline__ void cr_tile_xty(const double *__restrict__ X, const double *__restrict__ Y, int w, int a, int b, double (*As)[33], double (*Bs)[33], double acc[2][2]) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int r0 = 0; r0 < w; r0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 1024; e += 256) {
+            const int rr = e >> 5, cc = e & 31;
+            As[rr][cc] = __ldcg(X + (size_t)(r0 + rr) * w + 32 * a + cc);
+            Bs[rr][cc] = __ldcg(Y + (size_t)(r0 + rr) * w + 32 * b + cc);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr++) {
+            const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+    }
+}
+// the blocks that stay at this level: t = 2 s - 1 + 2 s u. blockIdx = u * (2 nt^2 + 1) + tile
+__global__ void __launch_bounds__(256) block_gram_kernel(CrPlan C, int s, int n_keep) {
+    __shared__ double As[32][33], Bs[32][33];
+    const int w = C.w, nt = w / 32, per = 2 * nt * nt + 1;
+    const int u = blockIdx.x / per;
+    int tile = blockIdx.x - u * per;
+    const int t = 2 * s - 1 + 2 * s * u, jl = t - s, jr = t + s;
+    const bool has_r = jr < C.K;
+    const size_t ww = (size_t)w * w;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    if (tile < nt * nt) {                                   // D_t, upper tiles only
+        const int a = tile / nt, b = tile - a * nt;
+        if (a > b) return;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        cr_tile_xty(C.Fb + jl * ww, C.Fb + jl * ww, w, a, b, As, Bs, acc);
+        if (has_r) cr_tile_xty(C.Fa + jr * ww, C.Fa + jr * ww, w, a, b, As, Bs, acc);
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) C.Dd[t * ww + (size_t)(32 * a + ty + 16 * p) * w + 32 * b + tx + 16 * q] -= acc[p][q];
+        return;
+    }
+    tile -= nt * nt;
+    if (tile < nt * nt) {                                   // new coupling (t, t + 2 s) = -Fa_{jr}^T Fb_{jr}
+        if (!has_r || t + 2 * s >= C.K) return;
+        const int a = tile / nt, b = tile - a * nt;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        cr_tile_xty(C.Fa + jr * ww, C.Fb + jr * ww, w, a, b, As, Bs, acc);
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) C.Cc[t * ww + (size_t)(32 * a + ty + 16 * p) * w + 32 * b + tx + 16 * q] = -acc[p][q];
+        return;
+    }
+    for (int c = tid; c < w; c += 256) {                    // g_t
+        double s0 = 0.0, s1 = 0.0;
+        const double *F = C.Fb + jl * ww, *yv = C.yy + (size_t)jl * w;
+        for (int r = 0; r < w; r++) s0 += __ldcg(F + (size_t)r * w + c) * __ldcg(yv + r);
+        if (has_r) {
+            F = C.Fa + jr * ww; yv = C.yy + (size_t)jr * w;
+            for (int r = 0; r < w; r++) s1 += __ldcg(F + (size_t)r * w + c) * __ldcg(yv + r);
+        }
+        C.gg[(size_t)t * w + c] -= s0 + s1;
+    }
+}
+
+// back phase: y_j -= Fa_j x_{j-s} + Fb_j x_{j+s} for the blocks eliminated at this level. warp = row
+__global__ void __launch_bounds__(256) block_apply_kernel(CrPlan C, int s, int cnt) {
+    const int lane = threadIdx.x & 31, w = C.w;
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= cnt * w) return;
+    const int j = s - 1 + 2 * s * (g / w), r = g % w;
+    double sum = 0.0;
+    if (j - s >= 0) {
+        const double *f = C.Fa + (size_t)j * w * w + (size_t)r * w, *xv = C.xx + (size_t)(j - s) * w;
+        for (int c = lane; c < w; c += 32) sum += __ldcg(f + c) * __ldcg(xv + c);
+    }
+    if (j + s < C.K) {
+        const double *f = C.Fb + (size_t)j * w * w + (size_t)r * w, *xv = C.xx + (size_t)(j + s) * w;
+        for (int c = lane; c < w; c += 32) sum += __ldcg(f + c) * __ldcg(xv + c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) C.yy[(size_t)j * w + r] -= sum;
+}

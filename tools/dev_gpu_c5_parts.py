@@ -8,10 +8,10 @@ p = synthetic.config(cfg, robust=False)
 print(f"poses {p.n_poses} points {p.n_points} obs {p.n_obs}", flush=True)
 s = problem.schedule_global_ba(20)
 base = None
-for parts, extra in [("2", {}), ("4", {}), ("6", {}), ("8", {}), ("12", {}), ("16", {}), ("2", {"BAGPU_NO_OVERLAP": "1"}), ("4", {"BAGPU_NO_OVERLAP": "1"}),
-                     ("8", {"BAGPU_NO_OVERLAP": "1"}), ("12", {"BAGPU_NO_OVERLAP": "1"}), ("16", {"BAGPU_NO_OVERLAP": "1"}), ("24", {"BAGPU_NO_OVERLAP": "1"})]:
+NO = {"BAGPU_NO_OVERLAP": "1"}
+for parts, extra in [("2", {}), ("2", NO), ("8", dict(NO, BAGPU_SEP_TILED="1")), ("8", NO), ("12", NO), ("16", NO), ("20", NO), ("24", NO), ("32", NO), ("16", {})]:
     os.environ["BAGPU_PARTS"] = parts
-    for k in ("BAGPU_NO_OVERLAP",):
+    for k in ("BAGPU_NO_OVERLAP", "BAGPU_SEP_TILED"):
         os.environ.pop(k, None)
     os.environ.update(extra)
     ctx = api.Context(0)
