@@ -1085,14 +1085,18 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
         // 13.5 ms per trial with two fronts, 16.0 / 17.7 ms with 4 / 8. The fronts pay off where the solve is exposed: after the
         // all-reduce of a multi-GPU trial, or when the overlap is off.
         if (overlap_possible) return BAGPU_OK;
-        // cost model (us; measured on B200, config 5: ~19 us per 32-column panel of the chain, ~40 us per panel of the separator system in
-        // the tiled solver, ~0.6 ms for the spikes, their products and the extra launches; the two-front solver runs at ~16 us per panel)
+        // cost model (us; measured on B200, config 5: ~19 us per 32-column panel of a front, ~160 us per level of the separator
+        // system's cyclic reduction, ~0.5 ms for the spikes, their products and the extra launches; the two-front solver runs at
+        // ~16 us per panel). More than ~100 SMs of spinning clusters slow each other down through L2 (16 fronts: 3.7 ms, 12: 2.8 ms).
         const double panels = n / 32.0, two_way = panels / 2 * 16.0 + 250.0;
         double best = 0.8 * two_way;
-        for (int q = 3; q <= PS_MAX_PARTS; q++) {
+        const int nc_guess = 8;
+        for (int q = 3; q <= PS_MAX_PARTS && q * nc_guess <= (2 * ctx->n_sm) / 3; q++) {
             const int per = interior_of(q);
             if (per < std::max(2 * w, 576)) break;
-            const double c = (per / 32.0 + w / 32.0) * 19.0 + (q - 1) * (w / 32.0) * 40.0 + 600.0;
+            int levels = 0;
+            while ((1 << levels) < q) levels++;
+            const double c = (per / 32.0 + w / 32.0) * 19.0 + levels * 160.0 + 500.0;
             if (c < best) { best = c; P = q; }
         }
         if (P < 3) return BAGPU_OK;
@@ -1354,7 +1358,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (sys_count + ctx->scratch_elems), st));      // system + y, y2, yM, row_done, fail
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
-            const bool overlap = !ctx->opt.no_overlap && !ctx->overlap_off && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0;
+            const bool overlap = !ctx->opt.no_overlap && !ctx->overlap_off && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0 &&
+                                 (!ctx->parts.on || ctx->parts.P * ctx->parts.nc <= ctx->n_sm / 4);     // many spinning clusters would starve pair_kernel
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
             ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = y1p; ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = fail_p;
             // the linear solve on stream sc: one cluster, or (two-way) two clusters from both ends of the band + the separator.
