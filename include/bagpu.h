@@ -120,11 +120,18 @@ typedef struct bagpu_schedule {
     const volatile uint8_t *stop_flag; /* the caller's bool* pbStopFlag, may be NULL; polled where g2o polls terminate() */
     int32_t linear_solver;          /* BAGPU_SOLVER_* */
     int32_t max_trace;              /* capacity of bagpu_result.trace (entries)            */
+    double  pcg_tolerance;          /* BAGPU_SOLVER_PCG: stop at |r| <= tol |b| (<= 0: 1e-10) */
+    int32_t pcg_max_iterations;     /* BAGPU_SOLVER_PCG: give up (= failed solve, rejected trial) after this many (<= 0: 20000) */
 } bagpu_schedule;
 
-#define BAGPU_SOLVER_AUTO     0     /* dense Cholesky when 6*Nc is small, PCG otherwise    */
-#define BAGPU_SOLVER_CHOLESKY 1     /* dense FP64 Cholesky of the reduced camera system    */
-#define BAGPU_SOLVER_PCG      2     /* block-Jacobi preconditioned CG on block-sparse Hschur */
+/* Reduced-camera-system solver (the seam of g2o::LinearSolver::solve, core/linear_solver.h:50-58).
+ * AUTO = CHOLESKY: the envelope (band) Cholesky family -- one front, two fronts from both ends, or P fronts with spikes and a
+ * cyclic-reduced separator system -- picked from the system's size; it is exact like the reference's SimplicialLDLT and, on the
+ * keyframe chains of this path, faster than PCG at every BASELINE size (DESIGN.md section 4 has the measurements).
+ * PCG = block-Jacobi preconditioned conjugate gradients on the band-stored Hschur, an opt-in alternative. */
+#define BAGPU_SOLVER_AUTO     0
+#define BAGPU_SOLVER_CHOLESKY 1
+#define BAGPU_SOLVER_PCG      2
 
 /* One entry per LM iteration = one OptimizationAlgorithmLevenberg::solve call
  * (this is also g2o's G2OBatchStatistics view, core/batch_stats.h:40-62). */

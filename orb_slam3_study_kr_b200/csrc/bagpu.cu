@@ -28,6 +28,7 @@
 #include "schur_pairs.cuh"
 #include "chol.cuh"
 #include "chol_parts.cuh"
+#include "pcg.cuh"
 #include "pose_opt.cuh"
 
 namespace {
@@ -174,6 +175,7 @@ struct bagpu_ctx {
         size_t s2_elems = 0, sM_elems = 0;
     } tw;
     PartPlan parts;                        // more than two fronts (long keyframe chains)
+    DevBuf d_pcg_vec, d_pcg_minv, d_pcg_part, d_pcg_scal;   // BAGPU_SOLVER_PCG work space
     DevBuf d_colend1, d_colend2, d_colendM, d_y2, d_SM, d_rhsM, d_zeroM, d_yM, d_xM, d_rowpos, d_rowofpos;
     char err[512] = {0};
     // ---- communicator (multi-GPU global BA)
@@ -468,6 +470,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel,
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
+                             (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
                              (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
@@ -508,6 +511,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
       for (DevBuf *x : tb) x->release(); }
     ctx->parts.release();
+    ctx->d_pcg_vec.release(); ctx->d_pcg_minv.release(); ctx->d_pcg_part.release(); ctx->d_pcg_scal.release();
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaStreamSynchronize(ctx->stream_chol);
@@ -1286,6 +1290,54 @@ int parts_enqueue_rest(bagpu_ctx *ctx, PartPlan &pp, const double *S, const doub
     return parts_launch_table(ctx, pp.d_tab.as<CholArgs>() + pp.P, pp.P, 1, pp.maxr, pp.n_max, lambda, nullptr, st);
 }
 
+// Block-Jacobi PCG on the band-stored reduced system (pcg.cuh). The host reads the residual every 25 iterations (one small D2H and
+// a sync); no convergence within max_iter, or a non-positive curvature, raises the failure flag = a rejected LM trial.
+int pcg_solve(bagpu_ctx *ctx, const double *S, int n, int ld, double lambda, const double *bp, const double *bs, double *x, int *failp,
+              double tol, int max_iter, int *iters_out) {
+    cudaStream_t st = ctx->stream;
+    const size_t nn = (size_t)n;
+    CK(ctx->d_pcg_vec.ensure(8 * 4 * nn)); CK(ctx->d_pcg_minv.ensure(8 * 36 * (nn / 6 + 1))); CK(ctx->d_pcg_part.ensure(8 * 3 * PCG_MAXB)); CK(ctx->d_pcg_scal.ensure(64));
+    PcgArgs A;
+    A.S = S; A.n = n; A.ld = ld; A.band = std::min(ld, n - 1); A.lambda = lambda; A.bp = bp; A.bs = bs; A.x = x;
+    A.r = ctx->d_pcg_vec.as<double>(); A.z = A.r + nn; A.p = A.z + nn; A.q = A.p + nn;
+    A.Minv = ctx->d_pcg_minv.as<double>(); A.part = ctx->d_pcg_part.as<double>(); A.scal = ctx->d_pcg_scal.as<double>();
+    const int ncam = n / 6;
+    A.nblk = std::max(1, std::min(PCG_MAXB, (ncam + PCG_THREADS - 1) / PCG_THREADS));
+    const int nblk_spmv = std::max(1, std::min(PCG_MAXB, (n + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
+    if (tol <= 0) tol = 1e-10;
+    if (max_iter <= 0) max_iter = 20000;
+    CK(cudaMemsetAsync(A.scal, 0, 64, st));
+    pcg_prec_kernel<<<(ncam + 127) / 128, 128, 0, st>>>(A, failp);
+    pcg_init_kernel<<<A.nblk, PCG_THREADS, 0, st>>>(A);
+    pcg_init_finish_kernel<<<1, PCG_THREADS, 0, st>>>(A);
+    int it = 0;
+    bool converged = false;
+    double h[8];
+    while (it < max_iter && !converged) {
+        const int chunk = std::min(25, max_iter - it);
+        for (int k = 0; k < chunk; k++) {
+            pcg_spmv_kernel<<<nblk_spmv, PCG_THREADS, 0, st>>>(A);
+            pcg_update_kernel<<<A.nblk, PCG_THREADS, 0, st>>>(A, nblk_spmv);
+            pcg_dir_kernel<<<A.nblk, PCG_THREADS, 0, st>>>(A);
+        }
+        it += chunk;
+        ctx->tm.total_launches += 3 * chunk;
+        CK(cudaMemcpyAsync(ctx->h_status.as<double>() + 16, A.scal, 64, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(h, ctx->h_status.as<double>() + 16, 64);
+        const double rr = h[3], bb = h[4];
+        if (!(rr == rr) || !(bb == bb)) break;                               // NaN: give up
+        if (bb == 0.0 || rr <= tol * tol * bb) converged = true;
+        if (!(h[1] > 0.0) && bb > 0.0) break;                                // p.q <= 0: not positive definite
+    }
+    if (!converged) { static const int one = 1; CK(cudaMemcpyAsync(failp, &one, sizeof(int), cudaMemcpyHostToDevice, st)); }
+    if (ctx->opt.debug) fprintf(stderr, "[bagpu] pcg: %d iterations, |r|/|b| = %.3e%s\n", it, (h[4] > 0) ? std::sqrt(h[3] / h[4]) : 0.0, converged ? "" : " (NOT converged)");
+    ctx->tm.pcg_iterations += it;
+    if (iters_out) *iters_out = it;
+    CK(cudaGetLastError());
+    return BAGPU_OK;
+}
+
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
     cudaStream_t st = ctx->stream;
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -1358,7 +1410,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             CK(cudaMemsetAsync(S, 0, sizeof(double) * (sys_count + ctx->scratch_elems), st));      // system + y, y2, yM, row_done, fail
             // Single GPU, band solver: the Cholesky cluster starts beside pair_kernel and consumes block columns as their camera
             // rows complete (row_done counters), so the accumulation of the reduced system hides behind the factorisation chain.
-            const bool overlap = !ctx->opt.no_overlap && !ctx->overlap_off && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0 &&
+            const bool use_pcg = s->linear_solver == BAGPU_SOLVER_PCG && n > 0;
+            const bool overlap = !use_pcg && !ctx->opt.no_overlap && !ctx->overlap_off && n > 0 && ctx->world == 1 && ctx->chol_maxr > 0 && ctx->n_items > 0 &&
                                  (!ctx->parts.on || ctx->parts.P * ctx->parts.nc <= ctx->n_sm / 4);     // many spinning clusters would starve pair_kernel
             CholArgs ca; ca.S = S; ca.n = n; ca.ld = ld; ca.lambda = lambda; ca.bp = bp; ca.bs = bs;
             ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = y1p; ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = fail_p;
@@ -1479,7 +1532,9 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             int rc = all_reduce_sum(ctx, S, sys_count); if (rc) return rc;
             if (overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             else if (n > 0) {
-                { ScopedEv ev(ctx, EV_LINSOLVE); rc = enqueue_solver_head(st, false); if (rc) return rc; rc = enqueue_solver_tail(st); if (rc) return rc; }
+                ScopedEv ev(ctx, EV_LINSOLVE);
+                if (use_pcg) { rc = pcg_solve(ctx, S, n, ld, lambda, bp, bs, ctx->d_xp.as<double>(), fail_p, s->pcg_tolerance, s->pcg_max_iterations, nullptr); if (rc) return rc; }
+                else { rc = enqueue_solver_head(st, false); if (rc) return rc; rc = enqueue_solver_tail(st); if (rc) return rc; }
             }
             pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), ctx->pose_cur, ctx->pose_trial,
                                                   ctx->d_xp.as<double>(), bp, lambda, dstat + 4);

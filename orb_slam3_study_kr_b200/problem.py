@@ -76,7 +76,8 @@ class CRound(C.Structure):
 class CSchedule(C.Structure):
     _fields_ = [("n_rounds", C.c_int32), ("rounds", C.c_void_p), ("delta_mono", C.c_double),
                 ("delta_stereo", C.c_double), ("lambda_init", C.c_double), ("stop_flag", C.c_void_p),
-                ("linear_solver", C.c_int32), ("max_trace", C.c_int32)]
+                ("linear_solver", C.c_int32), ("max_trace", C.c_int32),
+                ("pcg_tolerance", C.c_double), ("pcg_max_iterations", C.c_int32)]
 
 
 class CTrace(C.Structure):
@@ -162,6 +163,8 @@ class Schedule:
     linear_solver: int = SOLVER_AUTO
     max_trace: int = 256
     stop_flag: Optional[np.ndarray] = None      # uint8[1], written by another thread
+    pcg_tolerance: float = 0.0                  # SOLVER_PCG only (0: library default 1e-10)
+    pcg_max_iterations: int = 0
 
     def total_iterations(self) -> int:
         return sum(r.iterations for r in self.rounds)
@@ -172,7 +175,8 @@ class Schedule:
             rounds[i] = CRound(r.iterations, r.gate_after, r.gate_mono, r.gate_stereo,
                                int(r.drop_kernel_after), int(r.reset_pose))
         s = CSchedule(len(self.rounds), C.cast(rounds, C.c_void_p), self.delta_mono, self.delta_stereo,
-                      self.lambda_init, _ptr(self.stop_flag), self.linear_solver, self.max_trace)
+                      self.lambda_init, _ptr(self.stop_flag), self.linear_solver, self.max_trace,
+                      self.pcg_tolerance, self.pcg_max_iterations)
         return s, rounds
 
 

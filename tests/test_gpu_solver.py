@@ -111,3 +111,30 @@ def test_partitioned_solver_ill_conditioned_and_failure(ctx):
     assert fail
     with pytest.raises(api.BagpuError):
         ctx.test_solve(A[:600, :600], b[:600], np.minimum(599, ce[:600]), lam, parts=4)
+
+
+def test_pcg_solver_in_the_lm_loop(ctx):
+    """BAGPU_SOLVER_PCG (block-Jacobi PCG on the band-stored reduced system) behind the same seam: at a tight tolerance the LM
+    trajectory equals the direct solver's; the iteration count is reported; a hopeless iteration budget is a rejected trial
+    (failed linear solve), never an error."""
+    from orb_slam3_study_kr_b200 import problem, synthetic
+    p = synthetic.config(4, scale=0.25, robust=False)
+    s = problem.schedule_global_ba(6)
+    a = ctx.solve_ba(p, s)
+    s2 = problem.schedule_global_ba(6)
+    s2.linear_solver = problem.SOLVER_PCG
+    s2.pcg_tolerance = 1e-13
+    b = ctx.solve_ba(p, s2)
+    t = ctx.timing()
+    assert t["pcg_iterations"] > 0
+    assert [x["trials"] for x in a.trace] == [x["trials"] for x in b.trace]
+    for x, y in zip(a.trace, b.trace):
+        assert abs(x["chi2_after"] - y["chi2_after"]) <= 1e-8 * abs(x["chi2_after"])
+    assert np.abs(a.pose_qt - b.pose_qt).max() < 1e-6
+    s3 = problem.schedule_global_ba(2)
+    s3.linear_solver = problem.SOLVER_PCG
+    s3.pcg_tolerance = 1e-13
+    s3.pcg_max_iterations = 3
+    c = ctx.solve_ba(p, s3)
+    assert c.status == 1 and c.trace[0]["trials"] == 10        # ten rejected trials -> Terminate, as g2o does when the linear solver fails
+    assert np.array_equal(c.pose_qt[1:, :3], ctx.solve_ba(p, problem.schedule_global_ba(0)).pose_qt[1:, :3]) or np.isfinite(c.pose_qt).all()
