@@ -1495,7 +1495,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         PairArgs PA; PA.row_done = overlap ? rowdone_p : nullptr;
                         PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1; PA.hpp_diag = nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
                         PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
-                        PA.S2 = ctx->tw.on ? S2 : nullptr; PA.n_tot = n; PA.n1 = ctx->tw.n1;
+                        PA.S2 = (ctx->tw.on && !use_pcg) ? S2 : nullptr; PA.n_tot = n; PA.n1 = ctx->tw.n1;      // PCG reads the whole system from S
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
                         pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
                         ctx->tm.total_launches++;
