@@ -68,6 +68,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (h) return true;
@@ -78,6 +79,7 @@ struct NcclApi {
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        CommAbort = (decltype(CommAbort))dlsym(h, "ncclCommAbort");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
         return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
     }
@@ -494,7 +496,10 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    // Teardown must not depend on the peers: a rank that leaves early (an exception in the host code, a failed assertion in a test)
+    // would otherwise block in ncclCommDestroy while the others wait for it elsewhere. Every operation of this context has completed
+    // (stream synchronised above), so aborting the communicator only frees its resources.
+    if (ctx->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(ctx->comm); else if (g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm); }
     DevBuf *bufs[] = {&ctx->d_lm_ptr, &ctx->d_o_pose, &ctx->d_o_point, &ctx->d_o_meta, &ctx->d_o_u, &ctx->d_o_v, &ctx->d_o_ur, &ctx->d_o_w,
                       &ctx->d_cams, &ctx->d_rigs, &ctx->d_hidx, &ctx->d_perm, &ctx->d_raw8a, &ctx->d_raw8b, &ctx->d_raw16a, &ctx->d_raw16b,
                       &ctx->d_rawd, &ctx->d_pose_a, &ctx->d_pose_b, &ctx->d_pose_init, &ctx->d_pt_a, &ctx->d_pt_b, &ctx->d_pt_init, &ctx->d_meta_init, &ctx->d_sys, &ctx->d_xp, &ctx->d_y, &ctx->d_colend, &ctx->d_dinv, &ctx->d_widelist, &ctx->d_tasks, &ctx->d_Z, &ctx->d_Dr, &ctx->d_entries, &ctx->d_items, &ctx->d_pk_keys, &ctx->d_pk_keys2, &ctx->d_pk_vals,
