@@ -139,11 +139,47 @@ __global__ void __launch_bounds__(PS_THREADS) spike_forward_kernel(PartTable T, 
     }
 }
 
+// ---- FP64 tensor-core tile product (mma.sync.m8n8k4.f64 = DMMA): the spike products V^T V and F^T F are dense contractions over
+// thousands of rows, the one place on this path where the FP64 MMA pays (measured on this B200: 37.0 TFLOP/s against 33.7 for DFMA,
+// and one instruction per 256 multiply-adds instead of 8 per thread, so the loop is no longer bound by shared-memory loads).
+// out (32x32) += X[rows, xa .. xa + 31]^T  Y[rows, yb .. yb + 31], rows = [r_begin, r_end), X and Y row-major with leading dimension ldxy.
+// 256 threads: warp v owns the 8x8 sub-tiles (v >> 1, 2 (v & 1)) and (v >> 1, 2 (v & 1) + 1); a lane ends with elements
+// (lane / 4, 2 (lane % 4) + {0, 1}) of each. Shared tiles use a row stride of 36 doubles: the fragment loads are conflict-free.
+#define PS_TLD 36
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void tile_xty_dmma(const double *__restrict__ X, const double *__restrict__ Y, int ldxy, int r_begin, int r_end, int xa, int yb,
+                                              double (*As)[PS_TLD], double (*Bs)[PS_TLD], double c[2][2]) {
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int si = wv >> 1, sj = 2 * (wv & 1), fr = lane >> 2, fk = lane & 3;
+    for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 1024; e += 256) {
+            const int rr = e >> 5, cc = e & 31;
+            const bool in = r0 + rr < r_end;
+            As[rr][cc] = in ? __ldcg(X + (size_t)(r0 + rr) * ldxy + xa + cc) : 0.0;
+            Bs[rr][cc] = in ? __ldcg(Y + (size_t)(r0 + rr) * ldxy + yb + cc) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            const double a = As[k0 + fk][8 * si + fr];
+            const double b0 = Bs[k0 + fk][8 * sj + fr], b1 = Bs[k0 + fk][8 * sj + 8 + fr];
+            dmma_m8n8k4(c[0][0], c[0][1], a, b0);
+            dmma_m8n8k4(c[1][0], c[1][1], a, b1);
+        }
+    }
+}
+// where the lane's four results live inside the 32x32 tile: row, and column of c[q][0] (c[q][1] is the next column)
+#define PS_FRAG_ROW(tid) (8 * ((tid) >> 6) + (((tid) & 31) >> 2))
+#define PS_FRAG_COL(tid, q) (8 * (2 * (((tid) >> 5) & 1) + (q)) + 2 * ((tid) & 3))
+
 // Per partition i >= 1:  Dp_i = V_i^T V_i (upper 32x32 tiles),  Ep_i = V_i^T G_i^T (all tiles; G_i = L(T_{i+1}, I_i), only the last
 // rows of the interior reach it),  gp_i = V_i^T y_i.  CTA = one output tile, the whole sum in a fixed order.
 __global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const double *__restrict__ S, int ld, const double *__restrict__ V,
                                                          const double *__restrict__ y, double *__restrict__ Dp, double *__restrict__ Ep, double *__restrict__ gp) {
-    __shared__ double As[32][33], Bs[32][33];
+    __shared__ double As[32][PS_TLD], Bs[32][PS_TLD];
     int i = 1;
     while (i + 1 < T.P && T.d[i + 1].tile0 <= (int)blockIdx.x) i++;
     const PartDesc &D = T.d[i];
@@ -152,30 +188,17 @@ __global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const doub
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const double *Vp = V + D.v_off;
     const size_t so = (size_t)D.sep * w * w;
-    if (tile < ntri) {                                   // ---- Dp: tile (a, b), a <= b
+    if (tile < ntri) {                                   // ---- Dp: tile (a, b), a <= b, on the FP64 tensor pipe
         int a = 0;
         while (tile >= nt - a) { tile -= nt - a; a++; }
         const int b = a + tile;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        for (int r0 = 0; r0 < D.m; r0 += 32) {
-            __syncthreads();
-            for (int e = tid; e < 1024; e += 256) {
-                const int rr = e >> 5, cc = e & 31;
-                const bool in = r0 + rr < D.m;
-                As[rr][cc] = in ? __ldcg(Vp + (size_t)(r0 + rr) * w + 32 * a + cc) : 0.0;
-                Bs[rr][cc] = in ? __ldcg(Vp + (size_t)(r0 + rr) * w + 32 * b + cc) : 0.0;
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int rr = 0; rr < 32; rr++) {
-                const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
-                acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-            }
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        tile_xty_dmma(Vp, Vp, w, 0, D.m, 32 * a, 32 * b, As, Bs, c);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            double *o = Dp + so + (size_t)(32 * a + PS_FRAG_ROW(tid)) * w + 32 * b + PS_FRAG_COL(tid, q);
+            o[0] = c[q][0]; o[1] = c[q][1];
         }
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-#pragma unroll
-            for (int v = 0; v < 2; v++) Dp[so + (size_t)(32 * a + ty + 16 * u) * w + 32 * b + tx + 16 * v] = acc[u][v];
         return;
     }
     tile -= ntri;
@@ -409,56 +432,40 @@ __global__ void __launch_bounds__(PS_THREADS) block_spike_kernel(CrPlan C, int s
     }
 }
 
-// out (32x32 tile (a, b)) = X^T Y over the w rows, X and Y row-major w x w. 256 threads, 2x2 outputs each.
-__device__ __forceinline__ void cr_tile_xty(const double *__restrict__ X, const double *__restrict__ Y, int w, int a, int b, double (*As)[33], double (*Bs)[33], double acc[2][2]) {
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    for (int r0 = 0; r0 < w; r0 += 32) {
-        __syncthreads();
-        for (int e = tid; e < 1024; e += 256) {
-            const int rr = e >> 5, cc = e & 31;
-            As[rr][cc] = __ldcg(X + (size_t)(r0 + rr) * w + 32 * a + cc);
-            Bs[rr][cc] = __ldcg(Y + (size_t)(r0 + rr) * w + 32 * b + cc);
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int rr = 0; rr < 32; rr++) {
-            const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-        }
-    }
-}
 // the blocks that stay at this level: t = 2 s - 1 + 2 s u. blockIdx = u * (2 nt^2 + 1) + tile
 __global__ void __launch_bounds__(256) block_gram_kernel(CrPlan C, int s, int n_keep) {
-    __shared__ double As[32][33], Bs[32][33];
+    __shared__ double As[32][PS_TLD], Bs[32][PS_TLD];
     const int w = C.w, nt = w / 32, per = 2 * nt * nt + 1;
     const int u = blockIdx.x / per;
     int tile = blockIdx.x - u * per;
     const int t = 2 * s - 1 + 2 * s * u, jl = t - s, jr = t + s;
     const bool has_r = jr < C.K;
     const size_t ww = (size_t)w * w;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x;
     if (tile < nt * nt) {                                   // D_t, upper tiles only
         const int a = tile / nt, b = tile - a * nt;
         if (a > b) return;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        cr_tile_xty(C.Fb + jl * ww, C.Fb + jl * ww, w, a, b, As, Bs, acc);
-        if (has_r) cr_tile_xty(C.Fa + jr * ww, C.Fa + jr * ww, w, a, b, As, Bs, acc);
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        tile_xty_dmma(C.Fb + jl * ww, C.Fb + jl * ww, w, 0, w, 32 * a, 32 * b, As, Bs, c);
+        if (has_r) tile_xty_dmma(C.Fa + jr * ww, C.Fa + jr * ww, w, 0, w, 32 * a, 32 * b, As, Bs, c);
 #pragma unroll
-        for (int p = 0; p < 2; p++)
-#pragma unroll
-            for (int q = 0; q < 2; q++) C.Dd[t * ww + (size_t)(32 * a + ty + 16 * p) * w + 32 * b + tx + 16 * q] -= acc[p][q];
+        for (int q = 0; q < 2; q++) {
+            double *o = C.Dd + t * ww + (size_t)(32 * a + PS_FRAG_ROW(tid)) * w + 32 * b + PS_FRAG_COL(tid, q);
+            o[0] -= c[q][0]; o[1] -= c[q][1];
+        }
         return;
     }
     tile -= nt * nt;
     if (tile < nt * nt) {                                   // new coupling (t, t + 2 s) = -Fa_{jr}^T Fb_{jr}
         if (!has_r || t + 2 * s >= C.K) return;
         const int a = tile / nt, b = tile - a * nt;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        cr_tile_xty(C.Fa + jr * ww, C.Fb + jr * ww, w, a, b, As, Bs, acc);
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        tile_xty_dmma(C.Fa + jr * ww, C.Fb + jr * ww, w, 0, w, 32 * a, 32 * b, As, Bs, c);
 #pragma unroll
-        for (int p = 0; p < 2; p++)
-#pragma unroll
-            for (int q = 0; q < 2; q++) C.Cc[t * ww + (size_t)(32 * a + ty + 16 * p) * w + 32 * b + tx + 16 * q] = -acc[p][q];
+        for (int q = 0; q < 2; q++) {
+            double *o = C.Cc + t * ww + (size_t)(32 * a + PS_FRAG_ROW(tid)) * w + 32 * b + PS_FRAG_COL(tid, q);
+            o[0] = -c[q][0]; o[1] = -c[q][1];
+        }
         return;
     }
     for (int c = tid; c < w; c += 256) {                    // g_t
