@@ -26,6 +26,7 @@
 
 #include "ba_kernels.cuh"
 #include "schur_pairs.cuh"
+#include "schur_tiles.cuh"
 #include "chol.cuh"
 #include "chol_parts.cuh"
 #include "pcg.cuh"
@@ -122,6 +123,7 @@ struct BagpuOptions {
     bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
     int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
     bool sep_tiled = false;      // BAGPU_SEP_TILED: separator system through the tiled band solver instead of block cyclic reduction
+    bool pair_list = false;      // BAGPU_PAIR_LIST: pair_kernel over the per-pair entry list instead of pair_tile_kernel over (tile, landmark) records
     void read() {
         auto on = [](const char *k) { return getenv(k) != nullptr; };
         debug = on("BAGPU_DEBUG"); no_twoway = on("BAGPU_NO_TWOWAY"); compare = on("BAGPU_COMPARE"); no_tiles = on("BAGPU_NO_TILES");
@@ -131,7 +133,7 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
-        sep_tiled = on("BAGPU_SEP_TILED");
+        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST");
     }
 };
 
@@ -195,6 +197,10 @@ struct bagpu_ctx {
     DevBuf d_Z, d_Dr, d_entries, d_items, d_pk_keys, d_pk_keys2, d_pk_vals, d_npairs, d_pairoff, d_blkcnt, d_blkoff, d_itemcnt, d_itemoff, d_cubtmp, d_rowdone, d_part, d_blkdone, d_Lm;
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, updz_grid = 1, parts_stride = 1;
     int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
+    // tile-major Schur pass (schur_tiles.cuh): records sorted by tile, tile order, what the factorisation clusters wait on
+    bool tiles = false; int ntile = 0, tbw1 = 1;
+    DevBuf d_tp_raw, d_tp_recs, d_tp_idx, d_tp_idx2, d_tile_pos, d_tile_of_pos, d_cam_tpos;
+    int wait_bw1 = 1; const int *wait_rowpos = nullptr;    // item_off is indexed [wait_rowpos[camera] * wait_bw1 ..] by chol_band_kernel
     size_t s_elems = 0, scratch_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
@@ -473,7 +479,8 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
                              (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
-                             (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
+                             (const void *)pair_tile_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
+                             (const void *)tile_item_count_kernel, (const void *)tile_item_fill_kernel, (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
         // so a second context on another GPU of the same process gets its large dynamic shared memory and cluster sizes too.
@@ -516,6 +523,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
       for (DevBuf *x : tb) x->release(); }
     ctx->parts.release();
+    { DevBuf *tb2[] = {&ctx->d_tp_raw, &ctx->d_tp_recs, &ctx->d_tp_idx, &ctx->d_tp_idx2, &ctx->d_tile_pos, &ctx->d_tile_of_pos, &ctx->d_cam_tpos}; for (DevBuf *x : tb2) x->release(); }
     ctx->d_pcg_vec.release(); ctx->d_pcg_minv.release(); ctx->d_pcg_part.release(); ctx->d_pcg_scal.release();
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -832,8 +840,12 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         // order in which pair_kernel takes the camera rows: from both ends towards the separator when the factorisation is two-way
         // (built on the device: the plan stream must not queue H2D copies behind the bulk of the observation data)
         CK(ctx->d_rowpos.ensure(4 * (size_t)std::max(1, nf))); CK(ctx->d_rowofpos.ensure(4 * (size_t)std::max(1, nf)));
-        if (ctx->parts.on) row_order_parts_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->parts.T, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
-        else row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->tw.on ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
+        // (the interleaved orders only serve fronts that run BESIDE the accumulation; otherwise the natural order keeps the records of
+        // neighbouring rows together in L2)
+        const bool fronts_beside = ctx->world == 1 && !ctx->opt.no_overlap && !ctx->overlap_off;
+        if (ctx->parts.on && fronts_beside && ctx->parts.P * ctx->parts.nc <= ctx->n_sm / 4)
+            row_order_parts_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, ctx->parts.T, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
+        else row_order_kernel<<<grid_for(std::max(1, nf), 256), 256, 0, sp>>>(nf, (ctx->tw.on && fronts_beside) ? 1 : 0, ctx->d_rowpos.as<int>(), ctx->d_rowofpos.as<int>());
         if (ctx->opt.debug) fprintf(stderr, "[bagpu] n=%d band_blocks=%d band=%d ld=%d s_elems=%zu max_below=%d chol_grid=%d\n", n, bwb, band, ctx->ld, ctx->s_elems, max_below, ctx->chol_grid);
         CK(ctx->d_colend.ensure(sizeof(int) * (size_t)std::max(1, n)));
         CK(cudaMemcpyAsync(ctx->d_colend.p, col_end.data(), sizeof(int) * (size_t)std::max(1, n), cudaMemcpyHostToDevice, st));
@@ -863,18 +875,92 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sw, stage_wide_kernel, ST_THREADS, 0));
             ctx->stage_wide_grid = std::max(1, std::min(ctx->n_sm * std::max(1, occ_sw), (nw + ST_WARPS - 1) / ST_WARPS));
         }
-        ctx->n_items = 0; ctx->n_entries = 0;
+        ctx->n_items = 0; ctx->n_entries = 0; ctx->tiles = false;
         if (n > 0) {
+            CK(ctx->d_npairs.ensure(4 * (ne + 1))); CK(ctx->d_pairoff.ensure(4 * (ne + 1)));
+            unsigned *npairs = ctx->d_npairs.as<unsigned>(), *pairoff = ctx->d_pairoff.as<unsigned>();
+            int nblk = 0;
+            bool tiles = !ctx->opt.pair_list;
+            if (tiles) {
+                // (tile, landmark) records for pair_tile_kernel (schur_tiles.cuh), sorted by tile (stable radix sort of the records
+                // generated in observation order, so every tile's list is in landmark order).
+                const int ntile = (nf + TP_T - 1) / TP_T;
+                const int tbw1 = (ctx->band_blocks + TP_T - 1) / TP_T + 1;          // tB - tA <= (band_blocks + 3) / 4
+                const long long nblk_ll = (long long)ntile * tbw1;
+                if (nblk_ll >= (1ll << 31)) return fail(ctx, BAGPU_ERR_ARG, "reduced system has too many tiles (%lld)", nblk_ll);
+                nblk = (int)nblk_ll;
+                ctx->ntile = ntile; ctx->tbw1 = tbw1;
+                CK(ctx->d_tile_pos.ensure(4 * (size_t)ntile)); CK(ctx->d_tile_of_pos.ensure(4 * (size_t)ntile)); CK(ctx->d_cam_tpos.ensure(4 * (size_t)std::max(1, nf)));
+                CK(ctx->d_blkcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_blkoff.ensure(4 * ((size_t)nblk + 1)));
+                CK(ctx->d_itemcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_itemoff.ensure(4 * ((size_t)nblk + 1)));
+                CK(ctx->d_count.ensure(sizeof(unsigned long long) * 2));
+                unsigned *blkcnt = ctx->d_blkcnt.as<unsigned>(), *blkoff = ctx->d_blkoff.as<unsigned>();
+                unsigned *itemcnt = ctx->d_itemcnt.as<unsigned>(), *itemoff = ctx->d_itemoff.as<unsigned>();
+                int *ovf = reinterpret_cast<int *>(ctx->d_count.as<unsigned long long>() + 1);
+                tile_order_kernel<<<grid_for(ntile, 128), 128, 0, sp>>>(ntile, nf, ctx->d_rowpos.as<int>(), ctx->d_tile_pos.as<int>(), ctx->d_tile_of_pos.as<int>(), ctx->d_cam_tpos.as<int>());
+                CK(cudaMemsetAsync(blkcnt, 0, 4 * ((size_t)nblk + 1), sp));
+                CK(cudaMemsetAsync(npairs + ne, 0, 4, sp));
+                CK(cudaMemsetAsync(ovf, 0, sizeof(int), sp));
+                tile_plan_kernel<false><<<g, 256, 0, sp>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
+                                                           ctx->d_tile_pos.as<int>(), tbw1, npairs, blkcnt, nullptr, nullptr, nullptr, nullptr, ovf);
+                tile_item_count_kernel<<<grid_for(nblk + 1, 256), 256, 0, sp>>>(nblk + 1, blkcnt, itemcnt);
+                size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, npairs, pairoff, (int)(ne + 1), sp));
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, blkcnt, blkoff, nblk + 1, sp));
+                CK(ctx->d_cubtmp.ensure(std::max(tmp_a, tmp_b)));
+                size_t tmp = ctx->d_cubtmp.cap;
+                CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, npairs, pairoff, (int)(ne + 1), sp));
+                tmp = ctx->d_cubtmp.cap;
+                CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, blkcnt, blkoff, nblk + 1, sp));
+                tmp = ctx->d_cubtmp.cap;
+                CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp, itemcnt, itemoff, nblk + 1, sp));
+                unsigned totals[2] = {0, 0}; int h_ovf = 0;
+                CK(cudaMemcpyAsync(&totals[0], pairoff + ne, 4, cudaMemcpyDeviceToHost, sp));
+                CK(cudaMemcpyAsync(&totals[1], itemoff + nblk, 4, cudaMemcpyDeviceToHost, sp));
+                CK(cudaMemcpyAsync(&h_ovf, ovf, 4, cudaMemcpyDeviceToHost, sp));
+                CK(cudaStreamSynchronize(sp));
+                lap("tile count+scan+sync");
+                const size_t nrec = totals[0];
+                if (h_ovf || nrec >= (1ull << 31)) tiles = false;      // more than TP_MAX_LAYERS edges on one (pose, point) pair: the pair-list path takes any number
+                else {
+                    ctx->n_entries = (long long)nrec; ctx->n_items = (int)totals[1];
+                    if (nrec > 0) {
+                        CK(ctx->d_pk_keys.ensure(4 * nrec)); CK(ctx->d_pk_keys2.ensure(4 * nrec)); CK(ctx->d_tp_idx.ensure(4 * nrec)); CK(ctx->d_tp_idx2.ensure(4 * nrec));
+                        CK(ctx->d_tp_raw.ensure(sizeof(TileRec) * nrec)); CK(ctx->d_tp_recs.ensure(sizeof(TileRec) * nrec));
+                        CK(ctx->d_items.ensure(sizeof(TileItem) * (size_t)std::max(1, ctx->n_items)));
+                        tile_plan_kernel<true><<<g, 256, 0, sp>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
+                                                                  ctx->d_tile_pos.as<int>(), tbw1, nullptr, nullptr, pairoff, ctx->d_pk_keys.as<unsigned>(), ctx->d_tp_idx.as<unsigned>(),
+                                                                  ctx->d_tp_raw.as<TileRec>(), ovf);
+                        int end_bit = 1;
+                        while (end_bit < 32 && (1ll << end_bit) < nblk_ll) end_bit++;
+                        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_c, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
+                                                           ctx->d_tp_idx.as<unsigned>(), ctx->d_tp_idx2.as<unsigned>(), (int)nrec, 0, end_bit, sp));
+                        CK(ctx->d_cubtmp.ensure(tmp_c));
+                        tmp = ctx->d_cubtmp.cap;
+                        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, tmp, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
+                                                           ctx->d_tp_idx.as<unsigned>(), ctx->d_tp_idx2.as<unsigned>(), (int)nrec, 0, end_bit, sp));
+                        tile_gather_kernel<<<grid_for((int64_t)nrec, 256), 256, 0, sp>>>((unsigned)nrec, ctx->d_tp_idx2.as<unsigned>(), ctx->d_tp_raw.as<TileRec>(), ctx->d_tp_recs.as<TileRec>());
+                        tile_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, sp>>>(nblk, tbw1, ctx->d_tile_of_pos.as<int>(), blkoff, blkcnt, itemoff, ctx->d_items.as<TileItem>());
+                        CK(cudaGetLastError());
+                    }
+                    CK(ctx->d_part.ensure(sizeof(double) * TP_PART * (size_t)std::max(1, ctx->n_items)));
+                    int occ_p = 0;
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_tile_kernel, TP_THREADS, 0));
+                    ctx->pair_occ = std::max(1, occ_p);
+                    ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + TP_WARPS - 1) / TP_WARPS));
+                    ctx->tiles = true; ctx->wait_bw1 = tbw1; ctx->wait_rowpos = ctx->d_cam_tpos.as<int>();
+                }
+            }
+            if (!tiles) {
             // pair lists: for every upper block (a, b) of the reduced system the observation pairs (e_a, e_b) of the landmarks
             // both cameras see, sorted by block (stable radix sort of the pairs generated in observation order).
             const int bw1 = ctx->band_blocks + 1;
             const long long nblk_ll = (long long)nf * bw1;
             if (nblk_ll >= (1ll << 31)) return fail(ctx, BAGPU_ERR_ARG, "reduced system has too many blocks (%lld)", nblk_ll);
-            const int nblk = (int)nblk_ll;
-            CK(ctx->d_npairs.ensure(4 * (ne + 1))); CK(ctx->d_pairoff.ensure(4 * (ne + 1)));
+            nblk = (int)nblk_ll;
+            ctx->wait_bw1 = bw1; ctx->wait_rowpos = ctx->d_rowpos.as<int>();
             CK(ctx->d_blkcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_blkoff.ensure(4 * ((size_t)nblk + 1)));
             CK(ctx->d_itemcnt.ensure(4 * ((size_t)nblk + 1))); CK(ctx->d_itemoff.ensure(4 * ((size_t)nblk + 1)));
-            unsigned *npairs = ctx->d_npairs.as<unsigned>(), *pairoff = ctx->d_pairoff.as<unsigned>();
             unsigned *blkcnt = ctx->d_blkcnt.as<unsigned>(), *blkoff = ctx->d_blkoff.as<unsigned>();
             unsigned *itemcnt = ctx->d_itemcnt.as<unsigned>(), *itemoff = ctx->d_itemoff.as<unsigned>();
             CK(cudaMemsetAsync(blkcnt, 0, 4 * ((size_t)nblk + 1), sp));
@@ -918,19 +1004,22 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 pair_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, sp>>>(nblk, bw1, ctx->d_rowofpos.as<int>(), blkoff, blkcnt, itemoff, ctx->d_items.as<PairItem>());
                 CK(cudaGetLastError());
             }
+            }
             CK(ctx->d_Z.ensure(sizeof(double) * ZR_STRIDE * ne)); CK(ctx->d_Dr.ensure(sizeof(double) * DR_STRIDE * ne));
             CK(ctx->d_Lm.ensure(sizeof(double) * LM_STRIDE * (size_t)Np));
-            CK(ctx->d_part.ensure(sizeof(double) * PK_PART * (size_t)std::max(1, ctx->n_items)));
             CK(ctx->d_blkdone.ensure(sizeof(unsigned) * ((size_t)nblk + 1)));
             CK(cudaMemsetAsync(ctx->d_blkdone.p, 0, sizeof(unsigned) * ((size_t)nblk + 1), sp));
-            int occ_p = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, PK_THREADS, PK_SMEM_BYTES));
-            ctx->pair_occ = std::max(1, occ_p);
-            ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
+            if (!ctx->tiles) {
+                CK(ctx->d_part.ensure(sizeof(double) * PK_PART * (size_t)std::max(1, ctx->n_items)));
+                int occ_p = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, PK_THREADS, PK_SMEM_BYTES));
+                ctx->pair_occ = std::max(1, occ_p);
+                ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + PK_WARPS - 1) / PK_WARPS));
+            }
             CK(ctx->d_rowdone.ensure(sizeof(unsigned) * (size_t)std::max(1, nf)));
         }
-        if (ctx->opt.debug) fprintf(stderr, "[bagpu] pair plan: tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
-                                           ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
+        if (ctx->opt.debug) fprintf(stderr, "[bagpu] pair plan (%s): tasks=%d wide=%d entries=%lld items=%d stage_grid=%d pair_grid=%d\n",
+                                           ctx->tiles ? "tile records" : "pair list", ctx->n_tasks, nw, ctx->n_entries, ctx->n_items, ctx->stage_grid, ctx->pair_grid);
     }
     // [S | bp | bs | S2 | trial scratch: y (n), y2 (n2), yM (nM), row_done (nf x u32), fail | hpp_diag]: one memset per trial covers S .. fail
     ctx->scratch_elems = (size_t)std::max(1, n) + (size_t)ctx->tw.n2 + (size_t)ctx->tw.nM + ((size_t)std::max(1, nf) + 1) / 2 + 2;
@@ -952,7 +1041,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (ctx->parts.on) {
         const SysLayout L = sys_layout(ctx);
         int rcb = parts_bind(ctx, ctx->parts, L.S, L.bp, L.bs, L.y1, ctx->d_xp.as<double>(), ctx->d_dinv.as<double>(), L.fail,
-                             L.row_done, ctx->d_itemoff.as<unsigned>(), ctx->band_blocks + 1, ctx->d_rowpos.as<int>(), st);
+                             L.row_done, ctx->d_itemoff.as<unsigned>(), ctx->wait_bw1, ctx->wait_rowpos, st);
         if (rcb) return rcb;
     }
     lap("plan-rest");
@@ -1343,6 +1432,23 @@ int pcg_solve(bagpu_ctx *ctx, const double *S, int n, int ld, double lambda, con
     return BAGPU_OK;
 }
 
+// the camera half of the Schur complement: pair_tile_kernel over (tile, landmark) records, or pair_kernel over the pair list
+void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_done, double *hpp_diag, double *S2, int n1, cudaStream_t st) {
+    if (ctx->tiles) {
+        TileArgs A; A.items = ctx->d_items.as<TileItem>(); A.n_items = ctx->n_items; A.recs = ctx->d_tp_recs.as<TileRec>();
+        A.Z = ctx->d_Z.as<double>(); A.Dr = ctx->d_Dr.as<double>(); A.S = L.S; A.ld = ctx->ld; A.bp = L.bp; A.bs = L.bs;
+        A.part = ctx->d_part.as<double>(); A.blk_done = ctx->d_blkdone.as<unsigned>(); A.tbw1 = ctx->tbw1; A.tile_pos = ctx->d_tile_pos.as<int>();
+        A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag;
+        pair_tile_kernel<<<grid, TP_THREADS, 0, st>>>(A);
+        return;
+    }
+    PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
+    PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = L.S; PA.ld = ctx->ld; PA.bp = L.bp; PA.bs = L.bs;
+    PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1;
+    PA.row_done = row_done; PA.hpp_diag = hpp_diag; PA.S2 = S2; PA.n_tot = ctx->n_sys; PA.n1 = n1;
+    pair_kernel<<<grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+}
+
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
     cudaStream_t st = ctx->stream;
     BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
@@ -1384,11 +1490,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                     stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
                     n_part0 += ctx->stage_wide_grid; ctx->tm.total_launches++;
                 }
-                PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
-                PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
-                PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1;
-                PA.row_done = nullptr; PA.hpp_diag = hpp; PA.S2 = nullptr; PA.n_tot = n; PA.n1 = n;
-                pair_kernel<<<ctx->pair_grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+                launch_pair(ctx, L, ctx->pair_grid, nullptr, hpp, nullptr, n, st);
                 ctx->tm.total_launches++;
             } else {
                 BuildOut O; O.lambda = 0; O.mode = 0; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
@@ -1425,7 +1527,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             // (which must be queued before the stage to own their SMs) and everything that runs after pair_kernel has ended anyway.
             CholArgs c1, c2;
             auto enqueue_solver_head = [&](cudaStream_t sc, bool waits) -> int {
-                if (waits) { ca.row_done = rowdone_p; ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->band_blocks + 1; ca.row_pos = ctx->d_rowpos.as<int>(); }
+                if (waits) { ca.row_done = rowdone_p; ca.item_off = ctx->d_itemoff.as<unsigned>(); ca.bw1 = ctx->wait_bw1; ca.row_pos = ctx->wait_rowpos; }
                 if (ctx->parts.on) { ctx->tm.total_launches++; return parts_enqueue_factor(ctx, ctx->parts, lambda, waits ? rowdone_p : nullptr, sc); }
                 if (!ctx->tw.on) { ctx->tm.total_launches++; return launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, sc); }
                 const bagpu_ctx::TwoWay &T = ctx->tw;
@@ -1497,12 +1599,8 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
                     }
                     if (ctx->n_items > 0) {
-                        PairArgs PA; PA.row_done = overlap ? rowdone_p : nullptr;
-                        PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1; PA.hpp_diag = nullptr; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
-                        PA.Z = ctx->d_Z.as<double>(); PA.Dr = ctx->d_Dr.as<double>(); PA.S = S; PA.ld = ld; PA.bp = bp; PA.bs = bs;
-                        PA.S2 = (ctx->tw.on && !use_pcg) ? S2 : nullptr; PA.n_tot = n; PA.n1 = ctx->tw.n1;      // PCG reads the whole system from S
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
-                        pair_kernel<<<pgrid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+                        launch_pair(ctx, L, pgrid, overlap ? rowdone_p : nullptr, nullptr, (ctx->tw.on && !use_pcg) ? S2 : nullptr, ctx->tw.n1, st);      // PCG reads the whole system from S
                         ctx->tm.total_launches++;
                     }
                     if (overlap) {                     // the rest of the solve goes into the queue behind the factorisations

@@ -217,7 +217,8 @@ def test_solver_variants_agree():
 
     base = run({})
     for extra in ({"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_NO_TWOWAY": "1"}, {"BAGPU_NO_OVERLAP": "1", "BAGPU_NO_TWOWAY": "1"},
-                  {"BAGPU_UPDATE_RELIN": "1"}, {"BAGPU_NO_TILES": "1"}, {"BAGPU_STAGE_FIRST": "0"}):
+                  {"BAGPU_UPDATE_RELIN": "1"}, {"BAGPU_NO_TILES": "1"}, {"BAGPU_STAGE_FIRST": "0"}, {"BAGPU_PAIR_LIST": "1"},
+                  {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}):
         got = run(extra)
         assert got["trials"] == base["trials"], (extra, got["trials"], base["trials"])
         for a, b in zip(got["chi2"], base["chi2"]):
