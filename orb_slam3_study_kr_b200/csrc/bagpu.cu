@@ -123,6 +123,7 @@ struct BagpuOptions {
     bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
     int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
     bool sep_tiled = false;      // BAGPU_SEP_TILED: separator system through the tiled band solver instead of block cyclic reduction
+    bool tile_fma = false;       // BAGPU_TILE_FMA: the tile contraction with FMAs in registers (pair_tile_kernel) instead of the FP64 tensor pipe (pair_tile_mma_kernel)
     bool pair_list = false;      // BAGPU_PAIR_LIST: pair_kernel over the per-pair entry list instead of pair_tile_kernel over (tile, landmark) records
     void read() {
         auto on = [](const char *k) { return getenv(k) != nullptr; };
@@ -133,7 +134,7 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
-        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST");
+        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); tile_fma = on("BAGPU_TILE_FMA");
     }
 };
 
@@ -198,8 +199,8 @@ struct bagpu_ctx {
     int n_wide = 0, n_tasks = 0, stage_grid = 1, stage_wide_grid = 1, upd_grid = 1, updz_grid = 1, parts_stride = 1;
     int n_items = 0, pair_grid = 1, pair_occ = 1, stage_occ = 1; long long n_entries = 0;
     // tile-major Schur pass (schur_tiles.cuh): records sorted by tile, tile order, what the factorisation clusters wait on
-    bool tiles = false; int ntile = 0, tbw1 = 1;
-    DevBuf d_tp_raw, d_tp_recs, d_tp_idx, d_tp_idx2, d_tile_pos, d_tile_of_pos, d_cam_tpos;
+    bool tiles = false; int ntile = 0, tbw1 = 1, diag_grid = 1;
+    DevBuf d_tp_raw, d_tp_recs, d_tp_idx, d_tp_idx2, d_tile_pos, d_tile_of_pos, d_cam_tpos, d_tp_work;
     int wait_bw1 = 1; const int *wait_rowpos = nullptr;    // item_off is indexed [wait_rowpos[camera] * wait_bw1 ..] by chol_band_kernel
     size_t s_elems = 0, scratch_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
@@ -479,7 +480,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
                              (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
-                             (const void *)pair_tile_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
+                             (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
                              (const void *)tile_item_count_kernel, (const void *)tile_item_fill_kernel, (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
@@ -487,6 +488,8 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         if (cudaFuncGetAttributes(&fa, chol_band_kernel) == cudaSuccess) ctx->band_smem_cap = 232448 - fa.sharedSizeBytes - 1024;
         bool ok_attr = true;
         ok_attr &= cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(pair_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(pair_tile_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CH_MAX_SMEM_N)) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -523,7 +526,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
       for (DevBuf *x : tb) x->release(); }
     ctx->parts.release();
-    { DevBuf *tb2[] = {&ctx->d_tp_raw, &ctx->d_tp_recs, &ctx->d_tp_idx, &ctx->d_tp_idx2, &ctx->d_tile_pos, &ctx->d_tile_of_pos, &ctx->d_cam_tpos}; for (DevBuf *x : tb2) x->release(); }
+    { DevBuf *tb2[] = {&ctx->d_tp_raw, &ctx->d_tp_recs, &ctx->d_tp_idx, &ctx->d_tp_idx2, &ctx->d_tile_pos, &ctx->d_tile_of_pos, &ctx->d_cam_tpos, &ctx->d_tp_work}; for (DevBuf *x : tb2) x->release(); }
     ctx->d_pcg_vec.release(); ctx->d_pcg_minv.release(); ctx->d_pcg_part.release(); ctx->d_pcg_scal.release();
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -944,10 +947,13 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                         CK(cudaGetLastError());
                     }
                     CK(ctx->d_part.ensure(sizeof(double) * TP_PART * (size_t)std::max(1, ctx->n_items)));
+                    CK(ctx->d_tp_work.ensure(16)); CK(cudaMemsetAsync(ctx->d_tp_work.p, 0, 16, sp));
                     int occ_p = 0;
-                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_tile_kernel, TP_THREADS, 0));
+                    if (ctx->opt.tile_fma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_tile_kernel, TP_THREADS, TP_SMEM_BYTES));
+                    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_tile_mma_kernel, TP_THREADS, TM_SMEM_BYTES));
                     ctx->pair_occ = std::max(1, occ_p);
                     ctx->pair_grid = std::max(1, std::min(ctx->n_sm * ctx->pair_occ, (ctx->n_items + TP_WARPS - 1) / TP_WARPS));
+                    { int occ_d = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, tile_diag_kernel, TP_THREADS, 0)); ctx->diag_grid = std::max(1, ctx->n_sm * std::max(1, occ_d)); }
                     ctx->tiles = true; ctx->wait_bw1 = tbw1; ctx->wait_rowpos = ctx->d_cam_tpos.as<int>();
                 }
             }
@@ -1182,7 +1188,10 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
         // clusters take SMs away from pair_kernel and leave a longer tail (spikes + separator system) after it -- measured on config 5:
         // 13.5 ms per trial with two fronts, 16.0 / 17.7 ms with 4 / 8. The fronts pay off where the solve is exposed: after the
         // all-reduce of a multi-GPU trial, or when the overlap is off.
-        if (overlap_possible) return BAGPU_OK;
+        // One GPU: the two-front chain runs beside the accumulation, so P fronts only win when that chain is much longer than the pass it
+        // hides behind (config 5: two-front chain 7.7 ms -- 11 ms beside pair_tile_mma_kernel -- against a 5.2 ms pass + 2.7 ms of
+        // twelve fronts after it; config 4: 1.0 ms chain beside a 0.6 ms pass, two fronts stay).
+        const double pass_us = 0.28e-3 * (double)ctx->n_obs;
         // cost model (us; measured on B200, config 5: ~19 us per 32-column panel of a front, ~160 us per level of the separator
         // system's cyclic reduction, ~0.5 ms for the spikes, their products and the extra launches; the two-front solver runs at
         // ~16 us per panel). More than ~100 SMs of spinning clusters slow each other down through L2 (16 fronts: 3.7 ms, 12: 2.8 ms).
@@ -1198,6 +1207,7 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
             if (c < best) { best = c; P = q; }
         }
         if (P < 3) return BAGPU_OK;
+        if (overlap_possible && pass_us + best > 0.9 * std::max(pass_us, 1.4 * two_way)) return BAGPU_OK;
     }
     const int per = interior_of(P);
     PartTable &T = pp.T;
@@ -1438,8 +1448,11 @@ void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_don
         TileArgs A; A.items = ctx->d_items.as<TileItem>(); A.n_items = ctx->n_items; A.recs = ctx->d_tp_recs.as<TileRec>();
         A.Z = ctx->d_Z.as<double>(); A.Dr = ctx->d_Dr.as<double>(); A.S = L.S; A.ld = ctx->ld; A.bp = L.bp; A.bs = L.bs;
         A.part = ctx->d_part.as<double>(); A.blk_done = ctx->d_blkdone.as<unsigned>(); A.tbw1 = ctx->tbw1; A.tile_pos = ctx->d_tile_pos.as<int>();
-        A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag;
-        pair_tile_kernel<<<grid, TP_THREADS, 0, st>>>(A);
+        A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag; A.work = ctx->d_tp_work.as<unsigned>();
+        if (ctx->opt.tile_fma) { pair_tile_kernel<<<grid, TP_THREADS, TP_SMEM_BYTES, st>>>(A); return; }
+        // the Dr sums of the diagonal tiles first (they only need the stage's records), then the tiles on the FP64 tensor pipe
+        tile_diag_kernel<<<std::min(grid, ctx->diag_grid), TP_THREADS, 0, st>>>(A);
+        if (!hpp_diag) pair_tile_mma_kernel<<<grid, TP_THREADS, TM_SMEM_BYTES, st>>>(A);
         return;
     }
     PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();

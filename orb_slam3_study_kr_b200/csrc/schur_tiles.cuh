@@ -33,6 +33,11 @@
 #ifndef TP_MINB
 #define TP_MINB 3
 #endif
+#ifndef TP_STAGES
+#define TP_STAGES 6                        // depth of the per-warp cp.async ring (steps in flight)
+#endif
+#define TP_WARP_SMEM (TP_CHUNK * 32 + TP_STAGES * 16 * 96)     // the item's records | TP_STAGES x 16 Z records
+#define TP_SMEM_BYTES (TP_WARPS * TP_WARP_SMEM)
 #define TP_PART 720                        // doubles per item in the partial buffer: [36][16] block sums | [33][4] Dr sums | pad
 #define TP_MAX_LAYERS 32                   // edges on one (pose, point) pair the tile plan can express (more: pair_kernel path)
 
@@ -176,16 +181,25 @@ struct TileArgs {
     unsigned *row_done; int n_free;                      // optional: finished items per camera row (chol_band_kernel runs beside this kernel)
     double *S2; int n_tot, n1;    // optional (two-way factorisation): elements with column >= n1 go to the mirrored system S2
     double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit
+    unsigned *work;               // [2] next item / warps that ran out of items (zero at launch; the last warp out resets them)
 };
 
+BA_DEV void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+BA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> BA_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // acc (6x6, row-major) += Z_x Z_y^T with Z = [P^T Y; Y], P = -[X]x:  G = Y_x Y_y^T,  H = G P_y,  Z_x Z_y^T = [P_x^T H, P_x^T G; H, G]
-BA_DEV void tile_accumulate(const double *__restrict__ Z, int ex, int ey, double *acc) {
-    const double *px = Z + ZR_STRIDE * (size_t)ex, *py = Z + ZR_STRIDE * (size_t)ey;
+// a, b: the two 96-byte records (shared memory)
+BA_DEV void tile_accumulate(const double *__restrict__ pa, const double *__restrict__ pb, double *acc) {
     double a[ZR_STRIDE], b[ZR_STRIDE];
 #pragma unroll
-    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(py + 4 * i, b + 4 * i);
-#pragma unroll
-    for (int i = 0; i < ZR_STRIDE / 4; i++) ldg256(px + 4 * i, a + 4 * i);
+    for (int i = 0; i < ZR_STRIDE / 2; i++) {
+        const double2 va = reinterpret_cast<const double2 *>(pa)[i], vb = reinterpret_cast<const double2 *>(pb)[i];
+        a[2 * i] = va.x; a[2 * i + 1] = va.y; b[2 * i] = vb.x; b[2 * i + 1] = vb.y;
+    }
     const double ax = a[9], ay = a[10], az = a[11], bx = b[9], by = b[10], bz = b[11];
     double G[9], H[9];
 #pragma unroll
@@ -217,12 +231,18 @@ BA_DEV void tile_accumulate(const double *__restrict__ Z, int ex, int ey, double
 
 // d (33) += the Hpp / b_p / b_s terms of observation e:  Dr = [N (6) | m (3) | q (3)], X_l from the Z record.
 //   w B^T B = [P | I]^T N [P | I],  B^T g = [P^T m; m],  -Z L^-1 b_l = -[P^T q; q]
+BA_DEV void tile_diag_add(const double *v, double *d);
 BA_DEV void tile_diag_accumulate(const double *__restrict__ Dr, const double *__restrict__ Z, int e, double *d) {
     const double *pd = Dr + DR_STRIDE * (size_t)e;
-    double v[DR_STRIDE], zx[4];
+    double v[DR_STRIDE + 4];
 #pragma unroll
     for (int q = 0; q < DR_STRIDE / 4; q++) ldg256(pd + 4 * q, v + 4 * q);
-    ldg256(Z + ZR_STRIDE * (size_t)e + 8, zx);
+    ldg256(Z + ZR_STRIDE * (size_t)e + 8, v + DR_STRIDE);
+    tile_diag_add(v, d);
+}
+// v = [N (6) | m (3) | q (3) | y8 X_l (4)]
+BA_DEV void tile_diag_add(const double *v, double *d) {
+    const double *zx = v + DR_STRIDE;
     const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = zx[1], y = zx[2], z = zx[3];
     const double t00 = -z * n01 + y * n02, t01 = z * n00 - x * n02, t02 = -y * n00 + x * n01;
     const double t10 = -z * n11 + y * n12, t11 = z * n01 - x * n12, t12 = -y * n01 + x * n11;
@@ -241,27 +261,71 @@ BA_DEV void tile_diag_accumulate(const double *__restrict__ Dr, const double *__
 }
 
 __global__ void __launch_bounds__(TP_THREADS, TP_MINB) pair_tile_kernel(TileArgs P) {
+    extern __shared__ __align__(16) unsigned char tp_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane >> 4, ia = (lane >> 2) & 3, ib = lane & 3;
-    for (int it = blockIdx.x * TP_WARPS + warp; it < P.n_items; it += gridDim.x * TP_WARPS) {
+    int *srec = reinterpret_cast<int *>(tp_sm + (size_t)warp * TP_WARP_SMEM);                 // the item's records: [record][ea 0..3 | eb 0..3]
+    double *ring = reinterpret_cast<double *>(tp_sm + (size_t)warp * TP_WARP_SMEM + TP_CHUNK * 32);   // [stage][row: half h, ea 0..3 | eb 0..3][12]
+    // Items are taken from a counter, in plan order: the items of a diagonal tile (full chunks + the Dr pass) cost several times what a
+    // sparse off-diagonal tile's do, and a fixed stride can resonate with the period of a tile row (config 4: a few warps ran 3x longer
+    // than the average).
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = (int)atomicAdd(P.work, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= P.n_items) break;
         const TileItem I = P.items[it];
         const bool dt = I.ta == I.tb;
         if (P.hpp_diag && !dt) continue;
         const int ca = TP_T * I.ta + ia, cb = TP_T * I.tb + ib;                    // my block (lanes of the first half own the output)
         const bool blk_on = ca < P.n_free && cb < P.n_free && (!dt || ia <= ib);
         const bool multi = I.nit > 1;
+        const int nr = I.end - I.begin;
         double *mine = P.part + (size_t)it * TP_PART;
-        // ---- phase 1: the 16 blocks of the tile
+        __syncwarp();
+        {
+            const int4 *src = reinterpret_cast<const int4 *>(P.recs + I.begin);
+            int4 *dst = reinterpret_cast<int4 *>(srec);
+            for (int k = lane; k < 2 * nr; k += 32) dst[k] = __ldg(src + k);
+        }
+        __syncwarp();
+        // ---- phase 1: the 16 blocks of the tile. Two records per step; the 16 Z records a step needs are fetched once, by
+        // cp.async, TP_STAGES steps ahead of their use (two lanes per record), so the bytes in flight are not bounded by registers.
         if (!P.hpp_diag) {
             double acc[36];
 #pragma unroll
             for (int i = 0; i < 36; i++) acc[i] = 0.0;
-            const int *ra = &P.recs[I.begin].ea[ia], *rb = &P.recs[I.begin].eb[ib];
-            const int nr = I.end - I.begin;
-            for (int r = h; r < nr; r += 2) {
-                const int ea = __ldg(ra + 8 * r), eb = __ldg(rb + 8 * r);
-                if (blk_on && ea >= 0 && eb >= 0) tile_accumulate(P.Z, ea, eb, acc);
+            const int nsteps = (nr + 1) >> 1;
+            const int q = lane >> 1, hf = lane & 1;
+            auto issue = [&](int s, int stage) {
+                if (s < nsteps && 2 * s + (q >> 3) < nr) {
+                    const int idx = srec[16 * s + q];
+                    if (idx >= 0) {
+                        const double *src = P.Z + ZR_STRIDE * (size_t)idx + 6 * hf;
+                        double *dst = ring + (size_t)(stage * 16 + q) * ZR_STRIDE + 6 * hf;
+                        cp_async16(dst, src); cp_async16(dst + 2, src + 2); cp_async16(dst + 4, src + 4);
+                    }
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int s = 0; s < TP_STAGES - 1; s++) issue(s, s);
+            int st_use = 0, st_fill = TP_STAGES - 1;
+            for (int s = 0; s < nsteps; s++) {
+                issue(s + TP_STAGES - 1, st_fill);
+                cp_async_wait<TP_STAGES - 1>();
+                __syncwarp();
+                const int r = 2 * s + h;
+                if (r < nr) {
+                    const int ea = srec[8 * r + ia], eb = srec[8 * r + 4 + ib];
+                    if (blk_on && ea >= 0 && eb >= 0)
+                        tile_accumulate(ring + (size_t)(st_use * 16 + 8 * h + ia) * ZR_STRIDE, ring + (size_t)(st_use * 16 + 8 * h + 4 + ib) * ZR_STRIDE, acc);
+                }
+                __syncwarp();
+                st_use = (st_use + 1 == TP_STAGES) ? 0 : st_use + 1;
+                st_fill = (st_fill + 1 == TP_STAGES) ? 0 : st_fill + 1;
             }
+            cp_async_wait<0>();
 #pragma unroll
             for (int i = 0; i < 36; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
             if (multi) {
@@ -287,10 +351,8 @@ __global__ void __launch_bounds__(TP_THREADS, TP_MINB) pair_tile_kernel(TileArgs
         if (dt) {
 #pragma unroll
             for (int i = 0; i < 33; i++) d[i] = 0.0;
-            const int *ra = &P.recs[I.begin].ea[dc], *rb = &P.recs[I.begin].eb[dc];
-            const int nr = I.end - I.begin;
             for (int r = lane >> 2; r < nr; r += 8) {
-                const int ea = __ldg(ra + 8 * r), eb = __ldg(rb + 8 * r);
+                const int ea = srec[8 * r + dc], eb = srec[8 * r + 4 + dc];
                 if (ea >= 0 && ea == eb) tile_diag_accumulate(P.Dr, P.Z, ea, d);          // the (G, G) record of a group holds each observation once
             }
 #pragma unroll
@@ -370,5 +432,261 @@ __global__ void __launch_bounds__(TP_THREADS, TP_MINB) pair_tile_kernel(TileArgs
             __syncwarp();
             if (lane < 4 && dcam < P.n_free) atomicAdd(P.row_done + dcam, (unsigned)I.nit);
         }
+    }
+    if (lane == 0) {
+        const unsigned out = atomicAdd(P.work + 1, 1u);
+        if (out == gridDim.x * TP_WARPS - 1) { P.work[0] = 0u; P.work[1] = 0u; __threadfence(); }     // every warp has made its last grab
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pair_tile_mma_kernel: the same tile contraction on the FP64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA).
+//
+// Seen as a matrix product, a record adds  Z_A Z_B^T  to the 24 x 24 tile, with Z_A = the 6 x 3 blocks [P^T Y; Y] of the tile's four
+// cameras stacked (zero rows for a camera that does not see the landmark) and K = 3. Four records make K = 12 = three k-steps of
+// nine 8x8x4 DMMAs (six on a diagonal tile: the lower 8x8 tiles are not needed). Per group of four records a lane
+//   * fetches ONE raw Z record (its slot: record, side, camera) two groups ahead, into one of three register buffers,
+//   * expands it to the 6 x 3 block (18 FMAs) and stores it into the group's operand buffer in shared memory (double-buffered),
+//   * issues 27 (18) DMMAs on fragments read back from that buffer.
+// Against the FMA kernel above: 6.75 DMMA + 4.5 FP64 instructions per record instead of ~70 per record and half warp, 18 accumulator
+// registers instead of 72 (more warps per SM), and no idle lanes: an absent observation is a zero row, not a predicated-off lane.
+// The tensor pipe adds the k products of an instruction in a fixed order, so the result is reproducible like every other sum here.
+// The Dr sums of the diagonal tiles (Hpp, b_p, b_s) are a kernel of their own (tile_diag_kernel), launched before this one.
+//
+// Operand buffer: element (side, k, row) at side * TM_SIDE + k * TM_LDK + row + row / 6 (k-major, one pad row per camera): the
+// expansion stores (lanes = record x side x camera) and the fragment loads (lanes = row x k) are both free of bank conflicts
+// except for the half warps whose four rows straddle a camera boundary.
+#define TM_LDK 28
+#define TM_SIDE (12 * TM_LDK + 8)
+#define TM_BUF (2 * TM_SIDE)
+#define TM_WARP_SMEM (2 * TM_BUF * 8)      // two buffers
+#define TM_SMEM_BYTES (TP_WARPS * TM_WARP_SMEM)
+#ifndef TM_MINB
+#define TM_MINB 3                          // 168 registers, no spills (4 CTAs at 128 registers spill and run slower)
+#endif
+
+BA_DEV void tp_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(TileArgs P) {
+    extern __shared__ __align__(16) unsigned char tp_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *E = reinterpret_cast<double *>(tp_sm + (size_t)warp * TM_WARP_SMEM);
+    const int s_rec = lane >> 3, s_col = lane & 7, s_side = s_col >> 2, s_i = s_col & 3;     // my slot of a group: record, ea[i] / eb[i]
+    const int fr = lane >> 2, fk = lane & 3;                                                  // fragment row / k (and output row / column pair)
+    const int st_off = s_side * TM_SIDE + 3 * s_rec * TM_LDK + 7 * s_i;                        // my 6 x 3 block: + d * TM_LDK + comp
+    const int f0 = fk * TM_LDK + fr + fr / 6, f1 = fk * TM_LDK + (8 + fr) + (8 + fr) / 6, f2 = fk * TM_LDK + (16 + fr) + (16 + fr) / 6;
+    const int *rec_int = reinterpret_cast<const int *>(P.recs);
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = (int)atomicAdd(P.work, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= P.n_items) break;
+        const TileItem I = P.items[it];
+        const bool dt = I.ta == I.tb;
+        const bool multi = I.nit > 1;
+        const int nr = I.end - I.begin;
+        double c[9][2];
+        // the tile's totals: one add per element of S (two on the diagonal blocks: the Dr sums of tile_diag_kernel), exact in any order
+        auto emit_tile = [&]() {
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int TA = t / 3, TB = t - 3 * TA;
+                if (dt && TA > TB) continue;
+                const int R24 = 8 * TA + fr, ja = R24 / 6, r = R24 - 6 * ja;
+                const int a2 = TP_T * I.ta + ja;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int C24 = 8 * TB + 2 * fk + q, jb = C24 / 6, cc = C24 - 6 * jb;
+                    const int b2 = TP_T * I.tb + jb;
+                    const double v = c[t][q];
+                    if (a2 >= P.n_free || b2 >= P.n_free || (dt && ja > jb) || (a2 == b2 && cc < r) || v == 0.0) continue;
+                    const int R = 6 * a2 + r, C = 6 * b2 + cc;
+                    double *dst = (P.S2 && C >= P.n1) ? P.S2 + (size_t)(P.n_tot - 1 - C) * P.ld + (P.n_tot - 1 - R) : P.S + (size_t)R * P.ld + C;
+                    atomicAdd(dst, -v);
+                }
+            }
+        };
+#pragma unroll
+        for (int t = 0; t < 9; t++) { c[t][0] = 0.0; c[t][1] = 0.0; }
+        const int ngroups = (nr + 3) >> 2;
+        const int *my_int = rec_int + (size_t)I.begin * 8 + 8 * s_rec + s_col;
+        auto load_idx = [&](int g) -> int { return (4 * g + s_rec < nr) ? __ldg(my_int + 32 * g) : -1; };
+        auto load_row = [&](int idx, double *raw) {                // an absent observation is a record of zeros (its rows of the operand are zero)
+            if (idx >= 0) {
+                const double *src = P.Z + ZR_STRIDE * (size_t)idx;
+                ldg256(src, raw); ldg256(src + 4, raw + 4); ldg256(src + 8, raw + 8);
+            } else {
+#pragma unroll
+                for (int i = 0; i < ZR_STRIDE; i++) raw[i] = 0.0;
+            }
+        };
+        // group g: expand `cur` (fetched two groups ago), start the fetch of group g + 2 into `fill`, 27 / 18 DMMAs
+        int idx_q = -1;                                        // index of my slot in group g + 2 (loaded one group earlier)
+        auto group = [&](int g, const double *cur, double *fill) {
+            double *buf = E + (g & 1) * TM_BUF + st_off;
+            {   // rows 7 i .. 7 i + 5 of my side, columns 3 rec .. 3 rec + 2;  [X]x y = (-z y1 + y y2, z y0 - x y2, -y y0 + x y1) per column y of Y
+                const double x = cur[9], y = cur[10], z = cur[11];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double u0 = cur[d], u1 = cur[3 + d], u2 = cur[6 + d];   // column d of Y (row-major: Y[i][d] = cur[3 i + d])
+                    double *o = buf + d * TM_LDK;
+                    o[0] = fma(y, u2, -(z * u1));
+                    o[1] = fma(z, u0, -(x * u2));
+                    o[2] = fma(x, u1, -(y * u0));
+                    o[3] = u0; o[4] = u1; o[5] = u2;
+                }
+            }
+            load_row(idx_q, fill);
+            idx_q = load_idx(g + 3);
+            __syncwarp();
+            const double *ea = E + (g & 1) * TM_BUF, *eb = ea + TM_SIDE;
+#pragma unroll
+            for (int ks = 0; ks < 3; ks++) {
+                const int ko = 4 * ks * TM_LDK;
+                const double a0 = ea[ko + f0], a1 = ea[ko + f1], a2 = ea[ko + f2];
+                const double b0 = eb[ko + f0], b1 = eb[ko + f1], b2 = eb[ko + f2];
+                tp_dmma(c[0][0], c[0][1], a0, b0); tp_dmma(c[1][0], c[1][1], a0, b1); tp_dmma(c[2][0], c[2][1], a0, b2);
+                tp_dmma(c[4][0], c[4][1], a1, b1); tp_dmma(c[5][0], c[5][1], a1, b2); tp_dmma(c[8][0], c[8][1], a2, b2);
+                if (!dt) { tp_dmma(c[3][0], c[3][1], a1, b0); tp_dmma(c[6][0], c[6][1], a2, b0); tp_dmma(c[7][0], c[7][1], a2, b1); }
+            }
+        };
+        double r0[ZR_STRIDE], r1[ZR_STRIDE], r2[ZR_STRIDE];
+        {
+            const int i0 = load_idx(0), i1 = load_idx(1);
+            idx_q = load_idx(2);
+            load_row(i0, r0); load_row(i1, r1);
+        }
+        for (int g = 0; g < ngroups; g += 3) {
+            group(g, r0, r2);
+            if (g + 1 < ngroups) group(g + 1, r1, r0);
+            if (g + 2 < ngroups) group(g + 2, r2, r1);
+        }
+        __syncwarp();
+        if (!multi) { emit_tile(); }
+        else {
+            // tiles cut into several items: the LAST finisher adds the partials in item order (one total per element reaches S)
+            double *mine = P.part + (size_t)it * TP_PART;
+#pragma unroll
+            for (int t = 0; t < 9; t++) { __stcg(mine + (2 * t) * 32 + lane, c[t][0]); __stcg(mine + (2 * t + 1) * 32 + lane, c[t][1]); }
+            __threadfence();
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(P.blk_done + (size_t)P.tile_pos[I.ta] * P.tbw1 + (I.tb - I.ta), 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if ((prev + 1u) % (unsigned)I.nit != 0u) continue;
+            __threadfence();
+#pragma unroll
+            for (int t = 0; t < 9; t++) { c[t][0] = 0.0; c[t][1] = 0.0; }
+            for (int k = 0; k < I.nit; k++) {
+                const double *pk = P.part + (size_t)(I.first + k) * TP_PART + lane;
+#pragma unroll
+                for (int t = 0; t < 9; t++) { c[t][0] += __ldcg(pk + (2 * t) * 32); c[t][1] += __ldcg(pk + (2 * t + 1) * 32); }
+            }
+            emit_tile();
+        }
+        if (P.row_done) {
+            __threadfence();
+            __syncwarp();
+            const int cam = TP_T * I.ta + lane;
+            if (lane < TP_T && cam < P.n_free) atomicAdd(P.row_done + cam, (unsigned)I.nit);
+        }
+    }
+    if (lane == 0) {
+        const unsigned out = atomicAdd(P.work + 1, 1u);
+        if (out == gridDim.x * TP_WARPS - 1) { P.work[0] = 0u; P.work[1] = 0u; __threadfence(); }
+    }
+}
+
+// Hpp, b_p, b_s of every camera (and, for computeLambdaInit, the diagonal of Hpp only): the Dr records of the diagonal tiles' items,
+// lane = (record of 8, camera). Runs BEFORE pair_tile_mma_kernel on the same stream (both count a tile's finished items in blk_done:
+// a launch adds nit per tile, so the counters stay multiples of nit between launches).
+__global__ void __launch_bounds__(TP_THREADS, 3) tile_diag_kernel(TileArgs P) {
+    const int lane = threadIdx.x & 31;
+    const int *rec_int = reinterpret_cast<const int *>(P.recs);
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = (int)atomicAdd(P.work + 2, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= P.n_items) break;
+        const TileItem I = P.items[it];
+        if (I.ta != I.tb) continue;
+        const bool multi = I.nit > 1;
+        const int nr = I.end - I.begin;
+        double d[33];
+        const int dc = lane & 3, dcam = TP_T * I.ta + dc;
+#pragma unroll
+        for (int i = 0; i < 33; i++) d[i] = 0.0;
+        const int *rp = rec_int + (size_t)I.begin * 8;
+        // the (G, G) record of a group holds each of its observations once. Index loads run four records ahead of the Dr gathers, and
+        // two gathers are in flight per lane: the kernel is a chain of dependent loads otherwise.
+        auto obs_of = [&](int r) -> int {
+            if (r >= nr) return -1;
+            const int ea = __ldg(rp + 8 * r + dc), eb = __ldg(rp + 8 * r + 4 + dc);
+            return (ea == eb) ? ea : -1;
+        };
+        int e0 = obs_of(lane >> 2), e1 = obs_of((lane >> 2) + 8);
+        for (int r = lane >> 2; r < nr; r += 16) {
+            const int n0 = obs_of(r + 16), n1 = obs_of(r + 24);
+            double v0[DR_STRIDE + 4], v1[DR_STRIDE + 4];
+            if (e0 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e0; ldg256(pd, v0); ldg256(pd + 4, v0 + 4); ldg256(pd + 8, v0 + 8); ldg256(P.Z + ZR_STRIDE * (size_t)e0 + 8, v0 + 12); }
+            if (e1 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e1; ldg256(pd, v1); ldg256(pd + 4, v1 + 4); ldg256(pd + 8, v1 + 8); ldg256(P.Z + ZR_STRIDE * (size_t)e1 + 8, v1 + 12); }
+            if (e0 >= 0) tile_diag_add(v0, d);
+            if (e1 >= 0) tile_diag_add(v1, d);
+            e0 = n0; e1 = n1;
+        }
+#pragma unroll
+        for (int i = 0; i < 33; i++) {
+            d[i] += __shfl_xor_sync(0xffffffffu, d[i], 4);
+            d[i] += __shfl_xor_sync(0xffffffffu, d[i], 8);
+            d[i] += __shfl_xor_sync(0xffffffffu, d[i], 16);
+        }
+        if (multi) {
+            double *mine = P.part + (size_t)it * TP_PART;
+            if (lane < 4) {
+#pragma unroll
+                for (int i = 0; i < 33; i++) __stcg(mine + 576 + 4 * i + lane, d[i]);
+            }
+            __threadfence();
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(P.blk_done + (size_t)P.tile_pos[I.ta] * P.tbw1, 1u);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if ((prev + 1u) % (unsigned)I.nit != 0u) continue;
+            __threadfence();
+            if (lane < 4) {
+#pragma unroll
+                for (int i = 0; i < 33; i++) d[i] = 0.0;
+                for (int k = 0; k < I.nit; k++) {
+                    const double *pk = P.part + (size_t)(I.first + k) * TP_PART + 576 + lane;
+#pragma unroll
+                    for (int i = 0; i < 33; i++) d[i] += __ldcg(pk + 4 * i);
+                }
+            }
+        }
+        if (lane < 4 && dcam < P.n_free) {
+            if (P.hpp_diag) {                                                        // computeLambdaInit: diagonal of Hpp only
+                P.hpp_diag[6 * dcam + 0] = d[0]; P.hpp_diag[6 * dcam + 1] = d[6]; P.hpp_diag[6 * dcam + 2] = d[11];
+                P.hpp_diag[6 * dcam + 3] = d[15]; P.hpp_diag[6 * dcam + 4] = d[18]; P.hpp_diag[6 * dcam + 5] = d[20];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 33; i++) {
+                    if (d[i] == 0.0) continue;
+                    if (i < 21) {
+                        int r = 0, t = i;
+                        while (t >= 6 - r) { t -= 6 - r; r++; }
+                        const int R = 6 * dcam + r, C = R + t;
+                        double *dst = (P.S2 && C >= P.n1) ? P.S2 + (size_t)(P.n_tot - 1 - C) * P.ld + (P.n_tot - 1 - R) : P.S + (size_t)R * P.ld + C;
+                        atomicAdd(dst, d[i]);
+                    } else if (i < 27) atomicAdd(P.bp + 6 * dcam + (i - 21), d[i]);
+                    else atomicAdd(P.bs + 6 * dcam + (i - 27), d[i]);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        const unsigned out = atomicAdd(P.work + 3, 1u);
+        if (out == gridDim.x * TP_WARPS - 1) { P.work[2] = 0u; P.work[3] = 0u; __threadfence(); }
     }
 }

@@ -11,10 +11,10 @@ p = synthetic.config(cfg, robust=False)
 print(f"config {cfg}: poses {p.n_poses} points {p.n_points} obs {p.n_obs}", flush=True)
 s = problem.schedule_global_ba(iters)
 base = None
-KEYS = ("BAGPU_PAIR_LIST", "BAGPU_NO_OVERLAP", "BAGPU_PARTS")
-variants = [{}, {"BAGPU_PAIR_LIST": "1"}, {"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}]
+KEYS = ("BAGPU_PAIR_LIST", "BAGPU_NO_OVERLAP", "BAGPU_PARTS", "BAGPU_TILE_FMA")
+variants = [{}, {"BAGPU_TILE_FMA": "1"}, {"BAGPU_PAIR_LIST": "1"}, {"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_TILE_FMA": "1", "BAGPU_NO_OVERLAP": "1"}, {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}]
 if cfg == 5:
-    variants += [{"BAGPU_NO_OVERLAP": "1", "BAGPU_PARTS": "12"}, {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1", "BAGPU_PARTS": "12"}]
+    variants = [{}, {"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_TILE_FMA": "1", "BAGPU_NO_OVERLAP": "1"}, {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}]
 for extra in variants:
     for k in KEYS:
         os.environ.pop(k, None)
