@@ -28,6 +28,21 @@ struct BaDev {
     double delta_mono, delta_stereo;
 };
 
+// Levenberg-Marquardt state on the device (chained mode: small maps run a whole optimize() without a host round trip per trial).
+// Every kernel of a trial reads lambda and which of the two state buffers is current from here; lm_decide_kernel takes the accept /
+// reject decision of OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:99-166) at the end of the trial.
+struct LmTraceDev { int round, iteration, trials, status; double chi2_before, chi2_after, lambda; };
+struct LmDev {
+    double lambda, ni, currentChi, iniChi, rho;
+    int flip;                     // 0: buffers (a, b) = (current, trial); 1: swapped (an accepted trial flips)
+    int qmax, it, nBad, first, done, status;
+    int iterations, round, n_trace, max_trace;
+    int trials, starved;
+};
+BA_DEV bool lm_done(const LmDev *lm) { return lm != nullptr && lm->done != 0; }
+template <typename T> BA_DEV T *lm_cur(const LmDev *lm, T *a, T *b) { return (lm != nullptr && lm->flip) ? b : a; }
+template <typename T> BA_DEV T *lm_trial(const LmDev *lm, T *a, T *b) { return (lm != nullptr && lm->flip) ? a : b; }
+
 #define BUILD_THREADS 256
 #define BUILD_WARPS (BUILD_THREADS / 32)
 
@@ -270,11 +285,26 @@ struct UpdateOut {
     double *part_chi2;            // [gridDim.x]
     double *part_scale;           // [gridDim.x]  sum over landmarks of x_l (lambda x_l + b_l)
     const int *lm_list; int n_list;   // optional: update_kernel then handles only these landmarks (the "wide" ones)
+    // chained mode: lambda and the current / trial roles of the two state buffers come from the device state
+    const LmDev *lm = nullptr;
+    const double *pose_a = nullptr, *pose_b = nullptr; double *pt_a = nullptr, *pt_b = nullptr;
 };
+// resolve the chained-mode indirection: (pose, pt) = current state, O.pose_trial / O.pt_trial = trial state, O.lambda
+BA_DEV bool update_resolve(UpdateOut &O, const double *&pose, const double *&pt) {
+    if (!O.lm) return true;
+    if (O.lm->done) return false;
+    O.lambda = O.lm->lambda;
+    const bool f = O.lm->flip != 0;
+    pose = f ? O.pose_b : O.pose_a; pt = f ? O.pt_b : O.pt_a;
+    O.pose_trial = f ? O.pose_a : O.pose_b; O.pt_trial = f ? O.pt_a : O.pt_b;
+    return true;
+}
 
-__global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const double *__restrict__ pose,
-                                                              const double *__restrict__ pt, UpdateOut O) {
+__global__ void __launch_bounds__(BUILD_THREADS) update_kernel(BaDev D, const double *__restrict__ pose_in,
+                                                              const double *__restrict__ pt_in, UpdateOut O) {
     __shared__ double s_chi[BUILD_WARPS], s_sc[BUILD_WARPS];
+    const double *pose = pose_in, *pt = pt_in;
+    if (!update_resolve(O, pose, pt)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * BUILD_WARPS + warp, nw = gridDim.x * BUILD_WARPS;
     double chi_acc = 0.0, sc_acc = 0.0;
@@ -529,10 +559,14 @@ __global__ void count_active_kernel(const uint32_t *meta, int64_t n, unsigned lo
 
 // Pose step: T_trial = exp(x_p) * T (types_six_dof_expmap.h:73-76) for free poses, copy for fixed ones;
 // pose part of computeScale. Single block, fixed-order reduction.
-__global__ void pose_update_kernel(int n_poses, const int *__restrict__ hidx, const double *__restrict__ pose,
-                                   double *pose_trial, const double *__restrict__ xp, const double *__restrict__ bp,
-                                   double lambda, double *scale_out) {
+__global__ void pose_update_kernel(int n_poses, const int *__restrict__ hidx, const double *__restrict__ pose_a,
+                                   double *pose_b, const double *__restrict__ xp, const double *__restrict__ bp,
+                                   double lambda, double *scale_out, const LmDev *lm = nullptr) {
     __shared__ double sh[1024];
+    if (lm_done(lm)) return;
+    if (lm) lambda = lm->lambda;
+    const double *pose = (lm && lm->flip) ? pose_b : pose_a;
+    double *pose_trial = (lm && lm->flip) ? const_cast<double *>(pose_a) : pose_b;
     double acc = 0.0;
     for (int i = threadIdx.x; i < n_poses; i += blockDim.x) {
         const Pose T = load_pose(pose + 7 * (size_t)i);
@@ -601,6 +635,83 @@ __global__ void finish_trial_kernel(TrialSums T) {
 }
 
 // out[perm[i]] = in[i]  (sorted order -> caller's edge order)
+// ---- chained mode (no host round trip per trial)
+// computeLambdaInit on the device: lambda = tau * max diagonal (dstat[2], from reduce_partials_kernel) or the caller's value
+__global__ void lm_init_kernel(LmDev *lm, const double *dstat, double lambda_user, int iterations, int round, int max_trace) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    lm->lambda = (lambda_user > 0) ? lambda_user : 1e-5 * dstat[2];
+    lm->ni = 2.0; lm->currentChi = 0.0; lm->iniChi = 0.0; lm->rho = 0.0;
+    lm->flip = 0; lm->qmax = 0; lm->it = 0; lm->nBad = 0; lm->first = 1; lm->done = (iterations <= 0) ? 1 : 0; lm->status = BAGPU_OK;
+    lm->iterations = iterations; lm->round = round; lm->n_trace = 0; lm->max_trace = max_trace; lm->trials = 0; lm->starved = 0;
+}
+// End of a trial: the three sums (as finish_trial_kernel, same fixed order) and the decision of
+// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:99-166) + the stop rules of
+// SparseOptimizer::optimize (sparse_optimizer.cpp:380-416) as bagpu.cu's host loop applies them.
+__global__ void lm_decide_kernel(TrialSums T, const double *pose_scale, LmDev *lm, LmTraceDev *trace) {
+    __shared__ double sh[256];
+    __shared__ double sums[3];
+    if (lm->done) return;
+    for (int q = 0; q < 3; q++) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < T.na[q]; i += 256) v += T.a[q][i];
+        if (T.b[q]) for (int i = threadIdx.x; i < T.nb[q]; i += 256) v += T.b[q][i];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sums[q] = sh[0];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    T.out[0] = sums[0]; T.out[1] = sums[1]; T.out[2] = sums[2];
+    const int failflag = T.fail[1] ? T.fail[1] : T.fail[0];
+    if (failflag >= 2) { lm->starved = 1; lm->done = 1; return; }          // cannot happen without the overlap; the host reports it
+    const bool ok2 = failflag == 0;
+    double currentChi = lm->currentChi, iniChi = lm->iniChi, lambda = lm->lambda, ni = lm->ni;
+    if (lm->first) { currentChi = sums[0]; iniChi = currentChi; lm->first = 0; }
+    const double tempChi = ok2 ? sums[1] : DBL_MAX;
+    double rho = currentChi - tempChi;
+    double scale = sums[2] + *pose_scale;
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - pow((2 * rho - 1), 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        const double scaleFactor = fmax(1. / 3., alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        lm->flip ^= 1;                                                     // discardTop(): the trial state becomes current
+    } else {
+        lambda *= ni;
+        ni *= 2;                                                           // pop()
+    }
+    int qmax = lm->qmax + 1;
+    lm->trials++;
+    lm->rho = rho;
+    if (!(rho < 0 && qmax < 10)) {                                         // the iteration ends
+        int stt = BAGPU_OK, nBad = lm->nBad;
+        if (qmax == 10 || rho == 0) stt = BAGPU_TERMINATE_TRIALS;
+        else {
+            if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+            if (nBad >= 3) stt = BAGPU_TERMINATE_NBAD;
+        }
+        lm->nBad = nBad;
+        if (lm->n_trace < lm->max_trace) {
+            LmTraceDev &t = trace[lm->n_trace++];
+            t.round = lm->round; t.iteration = lm->it; t.trials = qmax; t.status = stt; t.chi2_before = iniChi; t.chi2_after = currentChi; t.lambda = lambda;
+        }
+        lm->it++;
+        lm->status = stt;
+        lm->first = 1;
+        qmax = 0;
+        if (stt != BAGPU_OK || lm->it >= lm->iterations) lm->done = 1;
+    }
+    lm->qmax = qmax; lm->lambda = lambda; lm->ni = ni; lm->currentChi = currentChi; lm->iniChi = iniChi;
+}
+
 template <typename T>
 __global__ void scatter_perm_kernel(int64_t n, const int *__restrict__ perm, const T *__restrict__ in, T *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -123,6 +123,8 @@ struct BagpuOptions {
     bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
     int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
     bool sep_tiled = false;      // BAGPU_SEP_TILED: separator system through the tiled band solver instead of block cyclic reduction
+    bool no_chain = false;       // BAGPU_NO_CHAIN: host-stepped LM loop (one status read per trial) even for small maps
+    long long chain_obs = 600000; // BAGPU_CHAIN_OBS: largest map (observations) whose LM loop runs chained on the device
     bool tile_fma = false;       // BAGPU_TILE_FMA: the tile contraction with FMAs in registers (pair_tile_kernel) instead of the FP64 tensor pipe (pair_tile_mma_kernel)
     bool pair_list = false;      // BAGPU_PAIR_LIST: pair_kernel over the per-pair entry list instead of pair_tile_kernel over (tile, landmark) records
     void read() {
@@ -134,7 +136,8 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
-        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); tile_fma = on("BAGPU_TILE_FMA");
+        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); tile_fma = on("BAGPU_TILE_FMA"); no_chain = on("BAGPU_NO_CHAIN");
+        if (getenv("BAGPU_CHAIN_OBS")) chain_obs = atoll(getenv("BAGPU_CHAIN_OBS"));
     }
 };
 
@@ -205,6 +208,7 @@ struct bagpu_ctx {
     size_t s_elems = 0, scratch_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
+    DevBuf d_lm, d_lm_trace; PinBuf h_lm;      // chained mode: LM state and per-iteration records on the device
     std::vector<int> h_hidx;
     std::vector<int> h_colend, h_ce1, h_ce2, h_ceM;      // envelope arrays: kept alive, copied on the main stream without a sync
     double *pose_cur = nullptr, *pose_trial = nullptr, *pt_cur = nullptr, *pt_trial = nullptr;
@@ -480,7 +484,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
                              (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
-                             (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
+                             (const void *)lm_init_kernel, (const void *)lm_decide_kernel, (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
                              (const void *)tile_item_count_kernel, (const void *)tile_item_fill_kernel, (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
@@ -518,7 +522,7 @@ void bagpu_destroy(bagpu_ctx *ctx) {
                       &ctx->d_fail, &ctx->d_count, &ctx->p_pose0, &ctx->p_ptr, &ctx->p_cams, &ctx->p_rigs, &ctx->p_xw, &ctx->p_meta,
                       &ctx->p_u, &ctx->p_v, &ctx->p_ur, &ctx->p_w, &ctx->p_chi2, &ctx->p_out, &ctx->p_pose_out, &ctx->p_ninl, &ctx->p_fchi};
     for (DevBuf *b : bufs) b->release();
-    ctx->h_status.release(); ctx->h_stage.release();
+    ctx->h_status.release(); ctx->h_stage.release(); ctx->d_lm.release(); ctx->d_lm_trace.release(); ctx->h_lm.release();
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; i++) if (ctx->ev_phase[i]) cudaEventDestroy(ctx->ev_phase[i]);
     for (int i = 0; i < 4; i++) if (ctx->ev_tw[i]) cudaEventDestroy(ctx->ev_tw[i]);
@@ -1443,12 +1447,12 @@ int pcg_solve(bagpu_ctx *ctx, const double *S, int n, int ld, double lambda, con
 }
 
 // the camera half of the Schur complement: pair_tile_kernel over (tile, landmark) records, or pair_kernel over the pair list
-void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_done, double *hpp_diag, double *S2, int n1, cudaStream_t st) {
+void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_done, double *hpp_diag, double *S2, int n1, cudaStream_t st, const LmDev *lm = nullptr) {
     if (ctx->tiles) {
         TileArgs A; A.items = ctx->d_items.as<TileItem>(); A.n_items = ctx->n_items; A.recs = ctx->d_tp_recs.as<TileRec>();
         A.Z = ctx->d_Z.as<double>(); A.Dr = ctx->d_Dr.as<double>(); A.S = L.S; A.ld = ctx->ld; A.bp = L.bp; A.bs = L.bs;
         A.part = ctx->d_part.as<double>(); A.blk_done = ctx->d_blkdone.as<unsigned>(); A.tbw1 = ctx->tbw1; A.tile_pos = ctx->d_tile_pos.as<int>();
-        A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag; A.work = ctx->d_tp_work.as<unsigned>();
+        A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag; A.work = ctx->d_tp_work.as<unsigned>(); A.lm = lm;
         if (ctx->opt.tile_fma) { pair_tile_kernel<<<grid, TP_THREADS, TP_SMEM_BYTES, st>>>(A); return; }
         // the Dr sums of the diagonal tiles first (they only need the stage's records), then the tiles on the FP64 tensor pipe
         tile_diag_kernel<<<std::min(grid, ctx->diag_grid), TP_THREADS, 0, st>>>(A);
@@ -1460,6 +1464,150 @@ void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_don
     PA.part = ctx->d_part.as<double>(); PA.blk_done = ctx->d_blkdone.as<unsigned>(); PA.bw1 = ctx->band_blocks + 1;
     PA.row_done = row_done; PA.hpp_diag = hpp_diag; PA.S2 = S2; PA.n_tot = ctx->n_sys; PA.n1 = n1;
     pair_kernel<<<grid, PK_THREADS, PK_SMEM_BYTES, st>>>(PA);
+}
+
+// Chained mode: a whole optimize() of a small map without a host round trip per trial. lambda, the accept / reject decision, the
+// buffer swap and the stop rules live on the device (LmDev, lm_decide_kernel); the host queues trials a few at a time, reads the state
+// once per chunk (where it also polls the caller's stop flag) and stops queueing when the device reports the loop finished -- trials
+// queued beyond that point return at their first instruction. The solve runs after the accumulation on the same stream (no second
+// stream, no spinning clusters); maps with the two-way / partitioned solvers, PCG or more than one rank use the host-stepped loop.
+bool chain_eligible(const bagpu_ctx *ctx, const bagpu_schedule *s) {
+    return !ctx->opt.no_chain && ctx->world == 1 && ctx->tiles && !ctx->opt.tile_fma && !ctx->opt.no_tiles && !ctx->opt.compare && !ctx->opt.update_relin &&
+           s->linear_solver != BAGPU_SOLVER_PCG && !ctx->tw.on && !ctx->parts.on && ctx->n_sys > 0 && ctx->n_items > 0 && ctx->n_tasks > 0 &&
+           ctx->n_obs <= ctx->opt.chain_obs;
+}
+
+int optimize_chained(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
+    cudaStream_t st = ctx->stream;
+    BaDev D = make_dev(ctx, s->delta_mono, s->delta_stereo);
+    const int n = ctx->n_sys, G = ctx->build_grid, PS = ctx->parts_stride;
+    const SysLayout L = sys_layout(ctx);
+    double *parts = ctx->d_parts.as<double>();
+    double *part_chi_b = parts, *part_max = parts + PS, *part_chi_u = parts + 2 * PS, *part_scale = parts + 3 * PS, *part_chi_w = parts + 4 * PS,
+           *part_chi_uw = parts + 5 * PS, *part_scale_w = parts + 6 * PS;
+    double *dstat = ctx->d_status.as<double>();
+    auto stop = [&]() { return s->stop_flag && *s->stop_flag; };
+    *status_out = BAGPU_OK;
+    if (iterations <= 0) return BAGPU_OK;
+    if (stop()) { *status_out = BAGPU_STOPPED; return BAGPU_OK; }
+    CK(ctx->d_lm.ensure(sizeof(LmDev))); CK(ctx->h_lm.ensure(sizeof(LmDev) + sizeof(LmTraceDev) * (size_t)iterations));
+    CK(ctx->d_lm_trace.ensure(sizeof(LmTraceDev) * (size_t)iterations));
+    LmDev *lm = ctx->d_lm.as<LmDev>();
+    LmTraceDev *dtrace = ctx->d_lm_trace.as<LmTraceDev>();
+    double *pose_a = ctx->pose_cur, *pose_b = ctx->pose_trial, *pt_a = ctx->pt_cur, *pt_b = ctx->pt_trial;
+    StageArgs SA; SA.tasks = ctx->d_tasks.as<int2>(); SA.n_tasks = ctx->n_tasks; SA.lm_list = ctx->d_widelist.as<int>(); SA.n_list = ctx->n_wide;
+    SA.Z = ctx->d_Z.as<double>(); SA.Dr = ctx->d_Dr.as<double>(); SA.Lm = ctx->d_Lm.as<double>(); SA.fail = L.fail;
+    {   // computeLambdaInit: the same stage / diagonal kernels as the trials, lambda set on the device
+        CK(cudaMemsetAsync(L.hpp, 0, sizeof(double) * n, st));
+        cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+        cudaEventRecord(e0, st);
+        StageArgs S0 = SA; S0.lambda = 1.0; S0.part_chi2 = part_chi_b; S0.part_maxdiag = part_max;
+        stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, pose_a, pt_a, S0);
+        int n_part0 = ctx->stage_grid;
+        if (ctx->n_wide > 0) {
+            StageArgs SW = S0; SW.part_chi2 = part_chi_b + ctx->stage_grid; SW.part_maxdiag = part_max + ctx->stage_grid;
+            stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, pose_a, pt_a, SW);
+            n_part0 += ctx->stage_wide_grid; ctx->tm.total_launches++;
+        }
+        launch_pair(ctx, L, ctx->pair_grid, nullptr, L.hpp, nullptr, n, st);
+        cudaEventRecord(e1, st);
+        ctx->pending.push_back({e0, e1, EV_BUILD});
+        reduce_partials_kernel<<<1, 256, 0, st>>>(n_part0, part_chi_b, nullptr, part_max, nullptr, L.hpp, n, dstat);
+        lm_init_kernel<<<1, 32, 0, st>>>(lm, dstat, s->lambda_init, iterations, round, iterations);
+        ctx->tm.total_launches += 4;
+        ctx->tm.edge_linearisations += n_active;
+    }
+    struct TrialEv { cudaEvent_t e[4]; };
+    std::vector<TrialEv> tev;
+    auto enqueue_trial = [&]() -> int {
+        TrialEv T;
+        for (int k = 0; k < 4; k++) T.e[k] = get_event(ctx);
+        CK(cudaMemsetAsync(L.S, 0, sizeof(double) * (L.sys_count + ctx->scratch_elems), st));
+        cudaEventRecord(T.e[0], st);
+        StageArgs S1 = SA; S1.lambda = 0.0; S1.part_chi2 = part_chi_b; S1.part_maxdiag = nullptr; S1.lm = lm; S1.pose_b = pose_b; S1.pt_b = pt_b;
+        stage_kernel<<<ctx->stage_grid, ST_THREADS, 0, st>>>(D, pose_a, pt_a, S1);
+        if (ctx->n_wide > 0) {
+            StageArgs SW = S1; SW.part_chi2 = part_chi_w;
+            stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, pose_a, pt_a, SW);
+            ctx->tm.total_launches++;
+        }
+        launch_pair(ctx, L, ctx->pair_grid, nullptr, nullptr, nullptr, n, st, lm);
+        cudaEventRecord(T.e[1], st);
+        CholArgs ca; ca.S = L.S; ca.n = n; ca.ld = ctx->ld; ca.lambda = 0.0; ca.bp = L.bp; ca.bs = L.bs; ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = L.y1;
+        ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = L.fail; ca.lm = lm;
+        { int rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, st); if (rc) return rc; }
+        cudaEventRecord(T.e[2], st);
+        pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), pose_a, pose_b, ctx->d_xp.as<double>(), L.bp, 0.0, dstat + 4, lm);
+        UpdateOut U; U.lambda = 0.0; U.xp = ctx->d_xp.as<double>(); U.pose_trial = pose_b; U.pt_trial = pt_b;
+        U.edge_chi2 = ctx->d_chi2.as<double>(); U.part_chi2 = part_chi_u; U.part_scale = part_scale; U.lm_list = nullptr; U.n_list = 0;
+        U.lm = lm; U.pose_a = pose_a; U.pose_b = pose_b; U.pt_a = pt_a; U.pt_b = pt_b;
+        UpdateTasks K; K.tasks = ctx->d_tasks.as<int2>(); K.n_tasks = ctx->n_tasks;
+        update_z_kernel<<<ctx->updz_grid, ST_THREADS, 0, st>>>(D, pt_a, U, K, ctx->d_Z.as<double>(), ctx->d_Lm.as<double>());
+        const bool upd_wide = ctx->n_wide > 0;
+        if (upd_wide) {
+            UpdateOut UW = U; UW.part_chi2 = part_chi_uw; UW.part_scale = part_scale_w; UW.lm_list = ctx->d_widelist.as<int>(); UW.n_list = ctx->n_wide;
+            update_kernel<<<G, BUILD_THREADS, 0, st>>>(D, pose_a, pt_a, UW);
+            ctx->tm.total_launches++;
+        }
+        cudaEventRecord(T.e[3], st);
+        TrialSums TS;
+        TS.a[0] = part_chi_b; TS.na[0] = ctx->stage_grid; TS.b[0] = ctx->n_wide > 0 ? part_chi_w : nullptr; TS.nb[0] = ctx->stage_wide_grid;
+        TS.a[1] = part_chi_u; TS.na[1] = ctx->updz_grid; TS.b[1] = upd_wide ? part_chi_uw : nullptr; TS.nb[1] = G;
+        TS.a[2] = part_scale; TS.na[2] = ctx->updz_grid; TS.b[2] = upd_wide ? part_scale_w : nullptr; TS.nb[2] = G;
+        TS.fail = L.fail; TS.out = dstat;
+        lm_decide_kernel<<<1, 256, 0, st>>>(TS, dstat + 4, lm, dtrace);
+        ctx->tm.total_launches += 8;
+        tev.push_back(T);
+        CK(cudaGetLastError());
+        return BAGPU_OK;
+    };
+    LmDev h; memset(&h, 0, sizeof(h));
+    h.iterations = iterations;
+    bool stopped = false;
+    for (;;) {
+        const int chunk = std::max(1, std::min(4, iterations - h.it));
+        for (int k = 0; k < chunk; k++) { int rc = enqueue_trial(); if (rc) return rc; }
+        CK(cudaMemcpyAsync(ctx->h_lm.p, lm, sizeof(LmDev), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(&h, ctx->h_lm.p, sizeof(LmDev));
+        if (h.done) break;
+        if (stop()) { stopped = true; break; }
+    }
+    if (h.starved) return fail(ctx, BAGPU_ERR_CUDA, "reduced-system solve reported a wait time-out in chained mode");
+    // per-trial phase times (events on the library stream) -> call totals and the per-iteration records
+    std::vector<float> tb(h.trials, 0.f), ts(h.trials, 0.f), tu(h.trials, 0.f), tt(h.trials, 0.f);
+    for (int k = 0; k < h.trials && k < (int)tev.size(); k++) {
+        cudaEventElapsedTime(&tb[k], tev[k].e[0], tev[k].e[1]); cudaEventElapsedTime(&ts[k], tev[k].e[1], tev[k].e[2]);
+        cudaEventElapsedTime(&tu[k], tev[k].e[2], tev[k].e[3]); cudaEventElapsedTime(&tt[k], tev[k].e[0], tev[k].e[3]);
+        ctx->tm.build_ms += tb[k]; ctx->tm.build_launches++; ctx->tm.linsolve_ms += ts[k]; ctx->tm.linsolve_launches++;
+        ctx->tm.update_ms += tu[k]; ctx->tm.update_launches++;
+    }
+    resolve_events(ctx);
+    if (h.n_trace > 0) {
+        LmTraceDev *ht = reinterpret_cast<LmTraceDev *>(ctx->h_lm.as<char>() + sizeof(LmDev));
+        CK(cudaMemcpyAsync(ht, dtrace, sizeof(LmTraceDev) * (size_t)h.n_trace, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int k0 = 0;
+        for (int i = 0; i < h.n_trace; i++) {
+            const LmTraceDev &d = ht[i];
+            if (res && res->trace && res->n_trace < s->max_trace) {
+                bagpu_trace &t = res->trace[res->n_trace++];
+                t.round = round; t.iteration = d.iteration; t.chi2_before = d.chi2_before; t.chi2_after = d.chi2_after; t.lambda = d.lambda; t.trials = d.trials; t.status = d.status;
+                t.active_edges = n_active;
+                double b = 0, sv = 0, u = 0, w = 0;
+                for (int k = k0; k < k0 + d.trials && k < h.trials; k++) { b += tb[k]; sv += ts[k]; u += tu[k]; w += tt[k]; }
+                t.linearise_schur_us = 1e3 * b; t.linear_solve_us = 1e3 * sv; t.update_us = 1e3 * u; t.iteration_us = 1e3 * w;
+            }
+            k0 += d.trials;
+        }
+    }
+    ctx->tm.lm_iterations += h.it; ctx->tm.lm_trials += h.trials;
+    ctx->tm.edge_linearisations += n_active * (int64_t)h.trials; ctx->tm.edge_evaluations += n_active * (int64_t)h.trials;
+    if (h.flip) { std::swap(ctx->pose_cur, ctx->pose_trial); std::swap(ctx->pt_cur, ctx->pt_trial); }
+    int status = h.status;
+    if ((stopped || stop()) && status == BAGPU_OK) status = BAGPU_STOPPED;
+    *status_out = status;
+    return BAGPU_OK;
 }
 
 int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations, int64_t n_active, bagpu_result *res, int *status_out) {
@@ -1796,7 +1944,8 @@ int bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *
             any_active = v > 0.5;
         }
         if (any_active) {
-            int rc = optimize(ctx, s, k, rd.iterations, (int64_t)n_active, r, &status);
+            int rc = chain_eligible(ctx, s) ? optimize_chained(ctx, s, k, rd.iterations, (int64_t)n_active, r, &status)
+                                            : optimize(ctx, s, k, rd.iterations, (int64_t)n_active, r, &status);
             if (rc) return rc;
         }
         if (rd.gate_after != BAGPU_GATE_NONE || rd.drop_kernel_after) {

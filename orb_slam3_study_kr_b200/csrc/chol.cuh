@@ -54,6 +54,8 @@ struct CholArgs {
     // rows to wait for are counted from there); no_back = 1: factor every panel and return (the backward substitution runs later,
     // once the separator unknowns are known).
     int row_base = 0, no_back = 0;
+    // chained mode: lambda from the device-side LM state (and nothing to do once the loop has ended); ba_kernels.cuh's LmDev
+    const struct LmDev *lm = nullptr;
 };
 
 // One warp factors the 32x32 SPD block in shared memory (Ld[r][c], lower part), 8 columns at a time:
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_solve_kernel(CholArgs a) {
     const int nwork = max(1, (int)gridDim.x - 1);                // CTAs 0..nwork-1 do TRSM rows and update tiles
     const bool worker = (int)blockIdx.x < nwork;
     double *yv = (n <= CH_MAX_SMEM_N) ? ysm : a.y;
+    if (a.lm) { if (a.lm->done) return; a.lambda = a.lm->lambda; }      // uniform over the grid: before any grid / cluster barrier
 
     for (size_t j = gtid; j < (size_t)n; j += gthreads) S[j * ld + j] += a.lambda;
     if (ycta) for (int j = tid; j < n; j += CH_THREADS) yv[j] = a.bp[j] + a.bs[j];
@@ -495,6 +498,7 @@ __device__ __forceinline__ void rank32_update(double *Cb, const double *Lr, cons
 __global__ void __launch_bounds__(CB_THREADS, 1) chol_band_kernel(CholArgs a, int maxr, int dyn_doubles, const CholArgs *__restrict__ table) {
     cg::cluster_group cl = cg::this_cluster();
     const int NC = (int)cl.num_blocks(), o = (int)cl.block_rank();
+    if (a.lm) { if (a.lm->done) return; a.lambda = a.lm->lambda; }      // uniform over the grid: before any cluster barrier
     if (table) {      // the launch carries lambda and whether to wait for pair_kernel's row counters; everything else is per partition
         const double lam = a.lambda; const bool wait = a.row_done != nullptr;
         a = table[blockIdx.x / NC]; a.lambda = lam;

@@ -198,10 +198,20 @@ struct StageArgs {
     double *part_chi2;            // [gridDim.x]
     double *part_maxdiag;         // optional [gridDim.x]: max |Hll diagonal| (computeLambdaInit)
     int *fail;
+    const LmDev *lm = nullptr; const double *pose_b = nullptr, *pt_b = nullptr;   // chained mode: lambda / current buffers from the device state
 };
+BA_DEV bool stage_resolve(StageArgs &S, const double *&pose, const double *&pt) {
+    if (!S.lm) return true;
+    if (S.lm->done) return false;
+    S.lambda = S.lm->lambda;
+    if (S.lm->flip) { pose = S.pose_b; pt = S.pt_b; }
+    return true;
+}
 
-__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, const double *__restrict__ pose_in, const double *__restrict__ pt_in, StageArgs S) {
     __shared__ double s_chi[ST_WARPS], s_max[ST_WARPS];
+    const double *pose = pose_in, *pt = pt_in;
+    if (!stage_resolve(S, pose, pt)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0, max_acc = 0.0;
     bool bad = false;
@@ -263,8 +273,10 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_kernel(BaDev D, con
 }
 
 // the same for landmarks with more than 32 observations: warp = landmark, two passes over its chunks
-__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D, const double *__restrict__ pose, const double *__restrict__ pt, StageArgs S) {
+__global__ void __launch_bounds__(ST_THREADS, ST_MINB) stage_wide_kernel(BaDev D, const double *__restrict__ pose_in, const double *__restrict__ pt_in, StageArgs S) {
     __shared__ double s_chi[ST_WARPS], s_max[ST_WARPS];
+    const double *pose = pose_in, *pt = pt_in;
+    if (!stage_resolve(S, pose, pt)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0, max_acc = 0.0;
     bool bad = false;
@@ -507,9 +519,11 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
 // x_l = L^-T (L^-1 b_l - sum_obs Z^T x_p): one 160-byte record and 18 FMA per observation, three sums per landmark. Then the
 // same evaluation of every edge at the trial state as update_packed_kernel (computeActiveErrors + activeRobustChi2) and the
 // landmark part of computeScale.
-__global__ void __launch_bounds__(ST_THREADS, 3) update_z_kernel(BaDev D, const double *__restrict__ pt, UpdateOut O, UpdateTasks K,
+__global__ void __launch_bounds__(ST_THREADS, 3) update_z_kernel(BaDev D, const double *__restrict__ pt_in, UpdateOut O, UpdateTasks K,
                                                                  const double *__restrict__ Zr, const double *__restrict__ Lm) {
     __shared__ double s_chi[ST_WARPS], s_sc[ST_WARPS];
+    const double *pt = pt_in, *pose_unused = nullptr;
+    if (!update_resolve(O, pose_unused, pt)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0, sc_acc = 0.0;
     for (int t = blockIdx.x * ST_WARPS + warp; t < K.n_tasks; t += gridDim.x * ST_WARPS) {

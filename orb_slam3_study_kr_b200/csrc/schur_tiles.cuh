@@ -181,7 +181,8 @@ struct TileArgs {
     unsigned *row_done; int n_free;                      // optional: finished items per camera row (chol_band_kernel runs beside this kernel)
     double *S2; int n_tot, n1;    // optional (two-way factorisation): elements with column >= n1 go to the mirrored system S2
     double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit
-    unsigned *work;               // [2] next item / warps that ran out of items (zero at launch; the last warp out resets them)
+    unsigned *work;               // [4] next item / warps that ran out of items, per kernel (zero at launch; the last warp out resets them)
+    const LmDev *lm = nullptr;    // chained mode: nothing to do once the LM loop has ended
 };
 
 BA_DEV void cp_async16(void *smem_dst, const void *gsrc) {
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(Tile
     const int st_off = s_side * TM_SIDE + 3 * s_rec * TM_LDK + 7 * s_i;                        // my 6 x 3 block: + d * TM_LDK + comp
     const int f0 = fk * TM_LDK + fr + fr / 6, f1 = fk * TM_LDK + (8 + fr) + (8 + fr) / 6, f2 = fk * TM_LDK + (16 + fr) + (16 + fr) / 6;
     const int *rec_int = reinterpret_cast<const int *>(P.recs);
+    if (lm_done(P.lm)) return;
     for (;;) {
         int it = 0;
         if (lane == 0) it = (int)atomicAdd(P.work, 1u);
@@ -579,7 +581,22 @@ __global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(Tile
             __threadfence();
 #pragma unroll
             for (int t = 0; t < 9; t++) { c[t][0] = 0.0; c[t][1] = 0.0; }
-            for (int k = 0; k < I.nit; k++) {
+            // (the adds stay in item order; four items' loads are in flight at a time)
+            int k = 0;
+            for (; k + 4 <= I.nit; k += 4) {
+                double v[4][18];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double *pk = P.part + (size_t)(I.first + k + u) * TP_PART + lane;
+#pragma unroll
+                    for (int t = 0; t < 18; t++) v[u][t] = __ldcg(pk + t * 32);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int t = 0; t < 9; t++) { c[t][0] += v[u][2 * t]; c[t][1] += v[u][2 * t + 1]; }
+            }
+            for (; k < I.nit; k++) {
                 const double *pk = P.part + (size_t)(I.first + k) * TP_PART + lane;
 #pragma unroll
                 for (int t = 0; t < 9; t++) { c[t][0] += __ldcg(pk + (2 * t) * 32); c[t][1] += __ldcg(pk + (2 * t + 1) * 32); }
@@ -605,6 +622,7 @@ __global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(Tile
 __global__ void __launch_bounds__(TP_THREADS, 3) tile_diag_kernel(TileArgs P) {
     const int lane = threadIdx.x & 31;
     const int *rec_int = reinterpret_cast<const int *>(P.recs);
+    if (lm_done(P.lm)) return;
     for (;;) {
         int it = 0;
         if (lane == 0) it = (int)atomicAdd(P.work + 2, 1u);
@@ -655,14 +673,19 @@ __global__ void __launch_bounds__(TP_THREADS, 3) tile_diag_kernel(TileArgs P) {
             prev = __shfl_sync(0xffffffffu, prev, 0);
             if ((prev + 1u) % (unsigned)I.nit != 0u) continue;
             __threadfence();
-            if (lane < 4) {
+            // lane (slice, camera) adds every eighth item, then the slices are added in a fixed order (item order inside a slice)
 #pragma unroll
-                for (int i = 0; i < 33; i++) d[i] = 0.0;
-                for (int k = 0; k < I.nit; k++) {
-                    const double *pk = P.part + (size_t)(I.first + k) * TP_PART + 576 + lane;
+            for (int i = 0; i < 33; i++) d[i] = 0.0;
+            for (int k = lane >> 2; k < I.nit; k += 8) {
+                const double *pk = P.part + (size_t)(I.first + k) * TP_PART + 576 + dc;
 #pragma unroll
-                    for (int i = 0; i < 33; i++) d[i] += __ldcg(pk + 4 * i);
-                }
+                for (int i = 0; i < 33; i++) d[i] += __ldcg(pk + 4 * i);
+            }
+#pragma unroll
+            for (int i = 0; i < 33; i++) {
+                d[i] += __shfl_xor_sync(0xffffffffu, d[i], 4);
+                d[i] += __shfl_xor_sync(0xffffffffu, d[i], 8);
+                d[i] += __shfl_xor_sync(0xffffffffu, d[i], 16);
             }
         }
         if (lane < 4 && dcam < P.n_free) {
