@@ -17,11 +17,12 @@ carries both strong-scaling curves. A step = one Optimizer::GlobalBundleAdjustem
           HBM, timed with CUDA events on the library's stream, max over ranks.
   e2e     the same metric through the reference-facing C-ABI call bagpu_solve_ba with HOST buffers: H2D of the whole
           problem, solve, D2H of poses / points / per-edge chi2 / flags inside the timed region.
-  roofline  the linearise+Schur pass (stage_kernel + pair_kernel), the dominant kernel group of the library stream:
+  roofline  the linearise+Schur pass (stage_kernel + tile_diag_kernel + pair_tile_mma_kernel), the dominant kernel group of the library stream:
           algorithmic bytes per pass / mean pass duration (CUDA events around every pass in the timed region, on the
           library's stream) against the measured HBM copy bandwidth; roofline_fp64 reports the same pass against the FP64
-          throughput measured on the device (the Schur products are FP64 work). On one GPU the band Cholesky
-          runs BESIDE pair_kernel on a second stream, so the `kernels` shares overlap and sum to more than 1.
+          throughput measured on the device (the Schur products are FP64 work; they run on the FP64 tensor pipe,
+          mma.sync.m8n8k4.f64). On config 4 (one GPU) the two-front band Cholesky runs BESIDE the pass on a second stream, so the
+          `kernels` shares overlap and sum to more than 1; on config 5 the twelve-front solver runs after it.
   parity_check  before the timed region every run solves a small map (config 4 at 1/10 size, merge schedule: two rounds and
           a gate) sharded over the N ranks and compares rank 0's result with the CPU oracle (1e-6 on chi2 per iteration
           and on the estimates, identical trial counts and edge levels): the multi-GPU path is checked where it is timed.
@@ -373,9 +374,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     achieved = alg_bytes / (build_avg_ms * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "build_pass_traffic.json")
-    if os.path.exists(tf) and which == "c4" and world == 1:
+    if os.path.exists(tf) and world == 1:
         try:
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tf)).get(which, {}).get("dram_bytes_per_launch")     # ncu --set full capture of the same workload
         except Exception:
             traffic = None
     fp64 = ctx.fp64_peak()
@@ -408,7 +409,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 "gpu_launches": int(acc["total_launches"]),
                 "clocks": m["clocks"],
                 "parity_check": parity,
-                "roofline": {"kernel": "linearise+Schur pass: stage_kernel + pair_kernel (CUDA events around the two launches on the library stream; the band Cholesky runs beside pair_kernel on its own stream)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "linearise+Schur pass: stage_kernel + tile_diag_kernel + pair_tile_mma_kernel (CUDA events around the launches of a pass on the library stream)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": build_avg_ms,
                              "launches": int(acc["build_launches"]),

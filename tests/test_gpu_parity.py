@@ -218,13 +218,61 @@ def test_solver_variants_agree():
     base = run({})
     for extra in ({"BAGPU_NO_OVERLAP": "1"}, {"BAGPU_NO_TWOWAY": "1"}, {"BAGPU_NO_OVERLAP": "1", "BAGPU_NO_TWOWAY": "1"},
                   {"BAGPU_UPDATE_RELIN": "1"}, {"BAGPU_NO_TILES": "1"}, {"BAGPU_STAGE_FIRST": "0"}, {"BAGPU_PAIR_LIST": "1"},
-                  {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}):
+                  {"BAGPU_PAIR_LIST": "1", "BAGPU_NO_OVERLAP": "1"}, {"BAGPU_TILE_FMA": "1"}):
         got = run(extra)
         assert got["trials"] == base["trials"], (extra, got["trials"], base["trials"])
         for a, b in zip(got["chi2"], base["chi2"]):
             assert abs(a - b) <= 1e-9 * abs(b), (extra, a, b)
         assert abs(got["pose_sum"] - base["pose_sum"]) <= 1e-9 * base["pose_sum"], extra
         assert abs(got["point_sum"] - base["point_sum"]) <= 1e-9 * base["point_sum"], extra
+
+
+def test_chained_loop_equals_host_stepped_loop():
+    """Small maps run the LM loop chained on the device (lm_decide_kernel: the decisions of optimization_algorithm_levenberg.cpp:99-166
+    without a host round trip per trial); BAGPU_NO_CHAIN=1 runs the same map through the host-stepped loop. Same trials, levels and
+    status, chi2 to 1e-10 (the device's pow against libm's), on the rig map (config 3: two edges per (pose, point) pair) and on config 2."""
+    import json
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_variant_worker.py")
+
+    def run(extra):
+        env = dict(os.environ)
+        env.update(extra)
+        out = subprocess.run([sys.executable, worker], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    for cfg in ("3", "2"):
+        chained = run({"VARIANT_CONFIG": cfg})
+        stepped = run({"VARIANT_CONFIG": cfg, "BAGPU_NO_CHAIN": "1"})
+        listed = run({"VARIANT_CONFIG": cfg, "BAGPU_PAIR_LIST": "1"})          # pair-list path (always host-stepped)
+        for other in (stepped, listed):
+            assert chained["trials"] == other["trials"] and chained["levels"] == other["levels"] and chained["status"] == other["status"]
+            for a, b in zip(chained["chi2"], other["chi2"]):
+                assert abs(a - b) <= 1e-10 * abs(b), (cfg, a, b)
+            assert abs(chained["pose_sum"] - other["pose_sum"]) <= 1e-10 * other["pose_sum"]
+        assert chained["launches"] != stepped["launches"]                          # the two loops really are different code paths
+
+
+def test_many_edges_on_one_pose_point_pair(ctx):
+    """More edges on one (pose, point) pair than the tile plan expresses (TP_MAX_LAYERS = 32): the upload falls back to the pair list,
+    which takes any number; fewer go through the tile records as extra layers. Both against the oracle."""
+    base = synthetic.config(1, scale=0.05)
+    for copies in (3, 40):
+        e = int(np.flatnonzero(~base.pose_fixed[base.obs_pose])[7])
+        idx = np.concatenate([np.arange(base.n_obs), np.full(copies, e)])
+        jitter = np.concatenate([np.zeros(base.n_obs), 0.25 * np.arange(1, copies + 1)])
+        p = problem.BAProblem(base.pose_qt, base.pose_fixed, base.points, base.cameras, base.rigs, base.obs_pose[idx], base.obs_point[idx],
+                              base.obs_cam[idx], base.obs_rig[idx], base.obs_kind[idx], base.obs_flags[idx], base.obs_u[idx] + jitter,
+                              base.obs_v[idx], base.obs_ur[idx], base.obs_inv_sigma2[idx])
+        s = problem.schedule_local_ba()
+        ref = ba_ref.solve(p, s)
+        got = ctx.solve_ba(p, s)
+        assert [t["trials"] for t in got.trace] == [t["trials"] for t in ref.trace]
+        for a, b in zip(got.trace, ref.trace):
+            assert abs(a["chi2_after"] - b["chi2_after"]) <= 1e-6 * abs(b["chi2_after"])
+        assert np.abs(got.pose_qt - ref.pose_qt).max() < 1e-6 and np.abs(got.points - ref.points).max() < 1e-6
 
 
 def test_partitioned_solver_in_the_lm_loop():
