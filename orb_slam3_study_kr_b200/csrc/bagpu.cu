@@ -126,6 +126,10 @@ struct BagpuOptions {
     bool no_chain = false;       // BAGPU_NO_CHAIN: host-stepped LM loop (one status read per trial) even for small maps
     long long chain_obs = 600000; // BAGPU_CHAIN_OBS: largest map (observations) whose LM loop runs chained on the device
     bool tile_fma = false;       // BAGPU_TILE_FMA: the tile contraction with FMAs in registers (pair_tile_kernel) instead of the FP64 tensor pipe (pair_tile_mma_kernel)
+    bool chunks = false;         // BAGPU_CHUNKS: multi-GPU trial with the rows of the reduced system accumulated, all-reduced and factored in three chunks of fronts
+                                 // (measured on 2 GPUs, config 5: 81.6 ms per step against 78.8 with one all-reduce: every front is as long as the others, so a full
+                                 // front still follows the last collective, and the early fronts take SMs from pair_tile_mma_kernel -- off by default)
+    bool spike_v1 = false;       // BAGPU_SPIKE_V1: spike_forward_kernel without the cp.async prefetch of the panel operands
     bool pair_list = false;      // BAGPU_PAIR_LIST: pair_kernel over the per-pair entry list instead of pair_tile_kernel over (tile, landmark) records
     void read() {
         auto on = [](const char *k) { return getenv(k) != nullptr; };
@@ -136,7 +140,7 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
-        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); tile_fma = on("BAGPU_TILE_FMA"); no_chain = on("BAGPU_NO_CHAIN");
+        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); spike_v1 = on("BAGPU_SPIKE_V1"); chunks = on("BAGPU_CHUNKS"); tile_fma = on("BAGPU_TILE_FMA"); no_chain = on("BAGPU_NO_CHAIN");
         if (getenv("BAGPU_CHAIN_OBS")) chain_obs = atoll(getenv("BAGPU_CHAIN_OBS"));
     }
 };
@@ -176,6 +180,12 @@ struct bagpu_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_chol2 = nullptr;   // second half of the two-way factorisation
     cudaEvent_t ev_tw[4] = {nullptr, nullptr, nullptr, nullptr};
+    // multi-GPU trial of the partitioned solver: the rows of the reduced system are accumulated, all-reduced and factored chunk by chunk
+    // (chunk = a group of fronts): the collective of chunk k and its factorisation fronts run while pair_tile_mma_kernel is still on k + 1
+    static constexpr int kChunks = 3;
+    cudaStream_t stream_comm = nullptr, stream_front[kChunks] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[3 * kChunks + 2] = {};
+    struct ChunkPlan { bool on = false; int n = 0; int part0[kChunks + 1]; int item0[kChunks + 1]; size_t elem0[kChunks + 1]; } chunks;
     struct TwoWay {                        // band factored from both ends towards a separator block M
         bool on = false;
         int k = 0, rT = 0, n1 = 0, n2 = 0, nM = 0, ldM = 0;
@@ -467,6 +477,12 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&ctx->stream_chol2, cudaStreamNonBlocking, hi); }
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->ev_tw[i], cudaEventDisableTiming);
+    {
+        int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&ctx->stream_comm, cudaStreamNonBlocking, hi);
+        for (int i = 0; i < bagpu_ctx::kChunks; i++) cudaStreamCreateWithPriority(&ctx->stream_front[i], cudaStreamNonBlocking, hi);
+        for (auto &e : ctx->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev_phase[i]);
     {
         // Load every kernel now. With CUDA's lazy module loading the FIRST launch of a kernel may synchronise the context; a
@@ -481,7 +497,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)pair_count_kernel, (const void *)pair_gen_kernel, (const void *)pair_item_count_kernel, (const void *)pair_item_fill_kernel,
                              (const void *)stage_kernel, (const void *)stage_wide_kernel, (const void *)pair_kernel, (const void *)chol_band_kernel,
                              (const void *)chol_solve_kernel<true>, (const void *)chol_solve_kernel<false>, (const void *)pose_opt_kernel,
-                             (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
+                             (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_forward2_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
                              (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
                              (const void *)lm_init_kernel, (const void *)lm_decide_kernel, (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
@@ -499,6 +515,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem_cap) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(spike_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem_cap) == cudaSuccess;
         if (!ok_attr) { cudaGetLastError(); bagpu_destroy(ctx); return BAGPU_ERR_CUDA; }
     }
     memset(&ctx->tm, 0, sizeof(ctx->tm));
@@ -527,6 +544,9 @@ void bagpu_destroy(bagpu_ctx *ctx) {
     for (int i = 0; i < 4; i++) if (ctx->ev_phase[i]) cudaEventDestroy(ctx->ev_phase[i]);
     for (int i = 0; i < 4; i++) if (ctx->ev_tw[i]) cudaEventDestroy(ctx->ev_tw[i]);
     if (ctx->stream_chol2) { cudaStreamSynchronize(ctx->stream_chol2); cudaStreamDestroy(ctx->stream_chol2); }
+    if (ctx->stream_comm) { cudaStreamSynchronize(ctx->stream_comm); cudaStreamDestroy(ctx->stream_comm); }
+    for (auto &f : ctx->stream_front) if (f) { cudaStreamSynchronize(f); cudaStreamDestroy(f); }
+    for (auto &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     { DevBuf *tb[] = {&ctx->d_colend1, &ctx->d_colend2, &ctx->d_colendM, &ctx->d_y2, &ctx->d_SM, &ctx->d_rhsM, &ctx->d_zeroM, &ctx->d_yM, &ctx->d_xM, &ctx->d_rowpos, &ctx->d_rowofpos};
       for (DevBuf *x : tb) x->release(); }
     ctx->parts.release();
@@ -1054,6 +1074,27 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                              L.row_done, ctx->d_itemoff.as<unsigned>(), ctx->wait_bw1, ctx->wait_rowpos, st);
         if (rcb) return rcb;
     }
+    // multi-GPU trial in chunks of fronts: row / item / element boundaries (the items are in natural row order when the fronts do not
+    // run beside the accumulation)
+    ctx->chunks.on = false;
+    if (ctx->parts.on && ctx->world > 1 && ctx->tiles && !ctx->opt.tile_fma && ctx->opt.chunks && ctx->parts.P >= 2 * bagpu_ctx::kChunks && ctx->n_items > 0) {
+        bagpu_ctx::ChunkPlan &C = ctx->chunks;
+        C.n = bagpu_ctx::kChunks;
+        unsigned h_item[bagpu_ctx::kChunks + 1];
+        for (int k = 0; k <= C.n; k++) {
+            C.part0[k] = (int)((long long)ctx->parts.P * k / C.n);
+            const int row = (k == C.n) ? n : ctx->parts.T.d[C.part0[k]].r0;          // sub-system q owns rows [r0_q, r0_{q+1}): interior + bottom separator
+            C.elem0[k] = (size_t)row * (ctx->ld + 1);
+            const int tile = std::min(ctx->ntile, (row / 6) / TP_T);
+            CK(cudaMemcpyAsync(&h_item[k], ctx->d_itemoff.as<unsigned>() + (size_t)tile * ctx->tbw1, 4, cudaMemcpyDeviceToHost, sp));
+        }
+        CK(cudaStreamSynchronize(sp));
+        for (int k = 0; k <= C.n; k++) C.item0[k] = (int)h_item[k];
+        C.item0[C.n] = ctx->n_items;
+        C.on = true;
+        if (ctx->opt.debug) fprintf(stderr, "[bagpu r%d] chunked trial: fronts %d/%d/%d/%d items %d/%d/%d/%d\n", ctx->rank, C.part0[0], C.part0[1], C.part0[2], C.part0[3],
+                                    C.item0[0], C.item0[1], C.item0[2], C.item0[3]);
+    }
     lap("plan-rest");
     const double tw3 = wall();
     CK(cudaEventRecord(ctx->ev_join, sp));
@@ -1072,10 +1113,10 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
 // ------------------------------------------------------------------------------- solve
 namespace {
 
-int all_reduce_sum(bagpu_ctx *ctx, double *buf, size_t count) {
+int all_reduce_sum(bagpu_ctx *ctx, double *buf, size_t count, cudaStream_t stream = nullptr) {
     if (ctx->world <= 1) return BAGPU_OK;
     if (ctx->opt.debug) fprintf(stderr, "[bagpu r%d] allreduce sum %zu\n", ctx->rank, count);
-    CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, stream ? stream : ctx->stream));
     return BAGPU_OK;
 }
 int all_reduce_max(bagpu_ctx *ctx, double *buf, size_t count) {
@@ -1360,7 +1401,15 @@ int parts_enqueue_rest(bagpu_ctx *ctx, PartPlan &pp, const double *S, const doub
     const PartTable &T = pp.T;
     const int nsep = pp.P - 1, w = pp.w;
     panel_inverse_kernel<<<(pp.inv_panels + PS_INV_WARPS - 1) / PS_INV_WARPS, 32 * PS_INV_WARPS, 0, st>>>(T, S, pp.ld, pp.d_linv.as<double>(), pp.inv_panels);
-    spike_forward_kernel<<<pp.spike_ctas, PS_THREADS, 0, st>>>(T, S, pp.ld, pp.d_subce.as<int>(), pp.d_linv.as<double>(), pp.d_V.as<double>());
+    {
+        const int ldr = (std::max(32, pp.maxr - CH_NB) + 1) & ~1;                 // rows of L below a panel's diagonal block
+        const size_t sm2 = spike_forward2_smem(ldr);
+        if (!ctx->opt.spike_v1 && sm2 <= ctx->band_smem_cap) {
+            const int per = (w + PS2_NCOL - 1) / PS2_NCOL;
+            spike_forward2_kernel<<<nsep * per, PS2_THREADS, sm2, st>>>(T, S, pp.ld, pp.d_subce.as<int>(), pp.d_linv.as<double>(), pp.d_V.as<double>(), ldr, per);
+        } else
+            spike_forward_kernel<<<pp.spike_ctas, PS_THREADS, 0, st>>>(T, S, pp.ld, pp.d_subce.as<int>(), pp.d_linv.as<double>(), pp.d_V.as<double>());
+    }
     spike_gram_kernel<<<pp.gram_ctas, 256, 0, st>>>(T, S, pp.ld, pp.d_V.as<double>(), y, pp.d_Dp.as<double>(), pp.d_Ep.as<double>(), pp.d_gp.as<double>());
     const long long na = (long long)nsep * w * 2 * w;
     if (pp.cr) {
@@ -1447,7 +1496,9 @@ int pcg_solve(bagpu_ctx *ctx, const double *S, int n, int ld, double lambda, con
 }
 
 // the camera half of the Schur complement: pair_tile_kernel over (tile, landmark) records, or pair_kernel over the pair list
-void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_done, double *hpp_diag, double *S2, int n1, cudaStream_t st, const LmDev *lm = nullptr) {
+// parts_of_pass: 1 = the Dr sums of the diagonal tiles, 2 = the tiles themselves (items [item_begin, item_end), -1 = to the end), 3 = both
+void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_done, double *hpp_diag, double *S2, int n1, cudaStream_t st, const LmDev *lm = nullptr,
+                 int parts_of_pass = 3, int item_begin = 0, int item_end = -1) {
     if (ctx->tiles) {
         TileArgs A; A.items = ctx->d_items.as<TileItem>(); A.n_items = ctx->n_items; A.recs = ctx->d_tp_recs.as<TileRec>();
         A.Z = ctx->d_Z.as<double>(); A.Dr = ctx->d_Dr.as<double>(); A.S = L.S; A.ld = ctx->ld; A.bp = L.bp; A.bs = L.bs;
@@ -1455,8 +1506,9 @@ void launch_pair(bagpu_ctx *ctx, const SysLayout &L, int grid, unsigned *row_don
         A.row_done = row_done; A.n_free = ctx->n_free; A.S2 = S2; A.n_tot = ctx->n_sys; A.n1 = n1; A.hpp_diag = hpp_diag; A.work = ctx->d_tp_work.as<unsigned>(); A.lm = lm;
         if (ctx->opt.tile_fma) { pair_tile_kernel<<<grid, TP_THREADS, TP_SMEM_BYTES, st>>>(A); return; }
         // the Dr sums of the diagonal tiles first (they only need the stage's records), then the tiles on the FP64 tensor pipe
-        tile_diag_kernel<<<std::min(grid, ctx->diag_grid), TP_THREADS, 0, st>>>(A);
-        if (!hpp_diag) pair_tile_mma_kernel<<<grid, TP_THREADS, TM_SMEM_BYTES, st>>>(A);
+        if (parts_of_pass & 1) tile_diag_kernel<<<std::min(grid, ctx->diag_grid), TP_THREADS, 0, st>>>(A);
+        A.item_begin = item_begin; A.item_end = item_end;
+        if (!hpp_diag && (parts_of_pass & 2)) pair_tile_mma_kernel<<<grid, TP_THREADS, TM_SMEM_BYTES, st>>>(A);
         return;
     }
     PairArgs PA; PA.items = ctx->d_items.as<PairItem>(); PA.n_items = ctx->n_items; PA.entries = ctx->d_entries.as<int2>();
@@ -1727,6 +1779,7 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             BuildOut O; O.lambda = lambda; O.mode = 1; O.S = S; O.ld = ld; O.bp = bp; O.bs = bs; O.hpp_diag = hpp;
             O.part_chi2 = part_chi_b; O.part_maxdiag = part_max; O.lm_list = nullptr; O.n_list = 0;
             const bool tiled = n > 0 && !ctx->opt.no_tiles;
+            const bool chunked = tiled && ctx->chunks.on && ctx->parts.on && ctx->world > 1 && !use_pcg;
             ScopedEv *ev_solve = nullptr;                     // overlap: the solve's timing bracket spans stage and pair on the other stream
             bool have_wide_part = false;
             int n_part_b = G, n_part_w = G;
@@ -1759,7 +1812,27 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
                         stage_wide_kernel<<<ctx->stage_wide_grid, ST_THREADS, 0, st>>>(D, ctx->pose_cur, ctx->pt_cur, SW);
                         have_wide_part = true; n_part_w = ctx->stage_wide_grid; ctx->tm.total_launches++;
                     }
-                    if (ctx->n_items > 0) {
+                    if (ctx->n_items > 0 && chunked) {
+                        // multi-GPU, partitioned solver: Dr sums first (b_p, b_s and the Hpp blocks are complete after them), then the tiles chunk by
+                        // chunk of fronts; chunk k's rows are all-reduced on the communication stream and factored on their own stream while
+                        // pair_tile_mma_kernel works on chunk k + 1
+                        const bagpu_ctx::ChunkPlan &C = ctx->chunks;
+                        cudaEvent_t *ev = ctx->ev_chunk;
+                        launch_pair(ctx, L, ctx->pair_grid, nullptr, nullptr, nullptr, n, st, nullptr, 1);
+                        CK(cudaEventRecord(ev[0], st)); CK(cudaStreamWaitEvent(ctx->stream_comm, ev[0], 0));
+                        { int rcc = all_reduce_sum(ctx, bp, 2 * (size_t)n, ctx->stream_comm); if (rcc) return rcc; }
+                        for (int k = 0; k < C.n; k++) {
+                            launch_pair(ctx, L, ctx->pair_grid, nullptr, nullptr, nullptr, n, st, nullptr, 2, C.item0[k], C.item0[k + 1]);
+                            CK(cudaEventRecord(ev[1 + k], st)); CK(cudaStreamWaitEvent(ctx->stream_comm, ev[1 + k], 0));
+                            { int rcc = all_reduce_sum(ctx, S + C.elem0[k], C.elem0[k + 1] - C.elem0[k], ctx->stream_comm); if (rcc) return rcc; }
+                            CK(cudaEventRecord(ev[1 + C.n + k], ctx->stream_comm)); CK(cudaStreamWaitEvent(ctx->stream_front[k], ev[1 + C.n + k], 0));
+                            { int rcc = parts_launch_table(ctx, ctx->parts.d_tab.as<CholArgs>() + C.part0[k], C.part0[k + 1] - C.part0[k], ctx->parts.nc, ctx->parts.maxr,
+                                                           ctx->parts.n_max, lambda, nullptr, ctx->stream_front[k]); if (rcc) return rcc; }
+                            CK(cudaEventRecord(ev[1 + 2 * C.n + k], ctx->stream_front[k]));
+                            ctx->tm.total_launches += 2;
+                        }
+                        ctx->tm.total_launches++;
+                    } else if (ctx->n_items > 0) {
                         const int pgrid = std::max(1, std::min(ctx->pair_grid, sm_avail * ctx->pair_occ));
                         launch_pair(ctx, L, pgrid, overlap ? rowdone_p : nullptr, nullptr, (ctx->tw.on && !use_pcg) ? S2 : nullptr, ctx->tw.n1, st);      // PCG reads the whole system from S
                         ctx->tm.total_launches++;
@@ -1793,9 +1866,14 @@ int optimize(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int iterations,
             }
             ctx->tm.total_launches++;
             ctx->tm.edge_linearisations += n_active;
-            int rc = all_reduce_sum(ctx, S, sys_count); if (rc) return rc;
+            int rc = chunked ? BAGPU_OK : all_reduce_sum(ctx, S, sys_count); if (rc) return rc;
             if (overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-            else if (n > 0) {
+            else if (n > 0 && chunked) {
+                ScopedEv ev(ctx, EV_LINSOLVE);                  // from the end of the accumulation: what is left of the fronts, then spikes, separators, backward passes
+                for (int k = 0; k < ctx->chunks.n; k++) CK(cudaStreamWaitEvent(st, ctx->ev_chunk[1 + 2 * ctx->chunks.n + k], 0));
+                ctx->tm.total_launches += 8;
+                rc = parts_enqueue_rest(ctx, ctx->parts, S, bp, bs, y1p, ctx->d_xp.as<double>(), lambda, fail_p, st); if (rc) return rc;
+            } else if (n > 0) {
                 ScopedEv ev(ctx, EV_LINSOLVE);
                 if (use_pcg) { rc = pcg_solve(ctx, S, n, ld, lambda, bp, bs, ctx->d_xp.as<double>(), fail_p, s->pcg_tolerance, s->pcg_max_iterations, nullptr); if (rc) return rc; }
                 else { rc = enqueue_solver_head(st, false); if (rc) return rc; rc = enqueue_solver_tail(st); if (rc) return rc; }

@@ -139,6 +139,102 @@ __global__ void __launch_bounds__(PS_THREADS) spike_forward_kernel(PartTable T, 
     }
 }
 
+// spike_forward_kernel with the panel's operands prefetched (sm_100a: cp.async double buffering). The kernel above reads the inverted
+// diagonal block and the panel's rows of L straight from L2 inside every panel step, so a step is two or three exposed L2 round trips
+// (8.8 us per panel on config 5: 0.64 ms for 72 panels). Here panel c + 1's operands (32 x 32 inverse, up to maxr - 32 rows x 32
+// columns of L) stream into shared memory while panel c is applied, a CTA takes 16 right-hand sides (half as many re-reads of L), and
+// the trailing update uses two threads per row.  Dynamic shared memory: win [PS_WIN][17] | Li [2][32][33] | Lb [2][32][ldr].
+#define PS2_NCOL 16
+#define PS2_THREADS 512
+#define PS2_WP 17
+__device__ __forceinline__ void ps_cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ps_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ps_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+inline size_t spike_forward2_smem(int ldr) { return sizeof(double) * ((size_t)PS_WIN * PS2_WP + 2 * 32 * 33 + 2 * 32 * (size_t)ldr); }
+
+__global__ void __launch_bounds__(PS2_THREADS, 1) spike_forward2_kernel(PartTable T, const double *__restrict__ S, int ld, const int *__restrict__ sub_colend,
+                                                                        const double *__restrict__ linv, double *__restrict__ V, int ldr, int ctas_per_part) {
+    extern __shared__ double ps2_sm[];
+    double *win = ps2_sm;                                   // [PS_WIN][PS2_WP]: rows p0 .. of the right-hand sides, circular in the row index
+    double *Li = win + PS_WIN * PS2_WP;                     // [2][32][33]
+    double *Lb = Li + 2 * 32 * 33;                          // [2][32][ldr]: Lb[q][r] = L(p0 + 32 + r, p0 + q)
+    __shared__ double vp[32][PS2_NCOL];
+    const int i = 1 + (int)blockIdx.x / ctas_per_part;
+    const PartDesc &D = T.d[i];
+    const int t0 = ((int)blockIdx.x - (i - 1) * ctas_per_part) * PS2_NCOL;
+    const int tid = threadIdx.x;
+    const int *ce = sub_colend + D.ce_off;
+    const int rT = D.r0 - D.wT;
+    for (int e = tid; e < PS_WIN * PS2_NCOL; e += PS2_THREADS) {
+        const int r = e / PS2_NCOL, j = e - r * PS2_NCOL, t = t0 + j;
+        double v = 0.0;
+        if (r < D.m && t < D.wT && (D.r0 + r) - (rT + t) <= ld) v = __ldcg(S + (size_t)(rT + t) * ld + D.r0 + r);
+        win[r * PS2_WP + j] = v;
+    }
+    auto rows_below = [&](int c) { const int p0 = 32 * c, nb = min(32, D.m - p0); return max(0, min(D.m - 1, ce[p0 + nb - 1]) - (p0 + 32) + 1); };
+    auto prefetch = [&](int c, int buf) {
+        const int p0 = 32 * c, nb = min(32, D.m - p0);
+        const double *lp = linv + D.linv_off + (size_t)c * 1024;
+        double *li = Li + buf * 32 * 33;
+        for (int e = tid; e < 1024; e += PS2_THREADS) ps_cp_async8(li + (e >> 5) * 33 + (e & 31), lp + e);
+        const int R = rows_below(c);
+        double *lb = Lb + (size_t)buf * 32 * ldr;
+        for (int e = tid; e < 32 * R; e += PS2_THREADS) {
+            const int q = e / R, r = e - q * R;
+            if (q < nb) ps_cp_async8(lb + (size_t)q * ldr + r, S + (size_t)(D.r0 + p0 + q) * ld + D.r0 + p0 + 32 + r);
+            else lb[(size_t)q * ldr + r] = 0.0;
+        }
+        ps_cp_commit();
+    };
+    double *Vp = V + D.v_off;
+    prefetch(0, 0);
+    for (int c = 0; c < D.k; c++) {
+        const int p0 = 32 * c, nb = min(32, D.m - p0), buf = c & 1;
+        ps_cp_wait_all();
+        __syncthreads();                                   // panel c's operands are in place; everybody is done with the other buffer
+        if (c + 1 < D.k) prefetch(c + 1, buf ^ 1);
+        {   // v_p = L_pp^-1 win[p0 .. p0 + 31]: thread = (row, column)
+            const int r = tid >> 4, j = tid & 15;
+            const double *li = Li + buf * 32 * 33 + r * 33;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 32; q += 2) {
+                s0 += li[q] * win[((p0 + q) % PS_WIN) * PS2_WP + j];
+                s1 += li[q + 1] * win[((p0 + q + 1) % PS_WIN) * PS2_WP + j];
+            }
+            const double v = (r < nb) ? s0 + s1 : 0.0;
+            vp[r][j] = v;
+            if (r < nb && t0 + j < D.wT) Vp[(size_t)(p0 + r) * D.wT + t0 + j] = v;
+        }
+        __syncthreads();
+        {   // rows below the panel: win[row] -= L(row, p0 .. p0 + 31) v_p: thread = (row, half of the columns)
+            const int R = rows_below(c);
+            const double *lb = Lb + (size_t)buf * 32 * ldr;
+            for (int rr = tid >> 1; rr < R; rr += PS2_THREADS / 2) {
+                const int h8 = 8 * (tid & 1);
+                double *w = win + ((p0 + 32 + rr) % PS_WIN) * PS2_WP + h8;
+                double acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = w[j];
+#pragma unroll 8
+                for (int q = 0; q < 32; q++) {
+                    const double l = lb[(size_t)q * ldr + rr];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[j] -= l * vp[q][h8 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = acc[j];
+            }
+            // the 32 slots of this panel become rows p0 + PS_WIN ..: beyond the reach of A(I, T) (PS_WIN > band), so they start at zero
+            // (v_p has read them before the barrier above; the update does not touch them: R <= PS_WIN - 64)
+            if (tid < 32 * PS2_NCOL) win[((p0 + (tid >> 4)) % PS_WIN) * PS2_WP + (tid & 15)] = 0.0;
+        }
+    }
+}
+
 // ---- FP64 tensor-core tile product (mma.sync.m8n8k4.f64 = DMMA): the spike products V^T V and F^T F are dense contractions over
 // thousands of rows, the one place on this path where the FP64 MMA pays (measured on this B200: 37.0 TFLOP/s against 33.7 for DFMA,
 // and one instruction per 256 multiply-adds instead of 8 per thread, so the loop is no longer bound by shared-memory loads).
@@ -146,26 +242,36 @@ __global__ void __launch_bounds__(PS_THREADS) spike_forward_kernel(PartTable T, 
 // 256 threads: warp v owns the 8x8 sub-tiles (v >> 1, 2 (v & 1)) and (v >> 1, 2 (v & 1) + 1); a lane ends with elements
 // (lane / 4, 2 (lane % 4) + {0, 1}) of each. Shared tiles use a row stride of 36 doubles: the fragment loads are conflict-free.
 #define PS_TLD 36
+#define CR_MAXW 384                    // widest separator the block kernels (and the gp product) are sized for
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// The 32-row slabs of X and Y are double-buffered: slab s + 1 streams in (cp.async) while slab s is multiplied.
 __device__ __forceinline__ void tile_xty_dmma(const double *__restrict__ X, const double *__restrict__ Y, int ldxy, int r_begin, int r_end, int xa, int yb,
-                                              double (*As)[PS_TLD], double (*Bs)[PS_TLD], double c[2][2]) {
+                                              double (*As)[32][PS_TLD], double (*Bs)[32][PS_TLD], double c[2][2]) {
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int si = wv >> 1, sj = 2 * (wv & 1), fr = lane >> 2, fk = lane & 3;
-    for (int r0 = r_begin; r0 < r_end; r0 += 32) {
-        __syncthreads();
+    auto prefetch = [&](int r0, int b) {
         for (int e = tid; e < 1024; e += 256) {
             const int rr = e >> 5, cc = e & 31;
-            const bool in = r0 + rr < r_end;
-            As[rr][cc] = in ? __ldcg(X + (size_t)(r0 + rr) * ldxy + xa + cc) : 0.0;
-            Bs[rr][cc] = in ? __ldcg(Y + (size_t)(r0 + rr) * ldxy + yb + cc) : 0.0;
+            if (r0 + rr < r_end) {
+                ps_cp_async8(&As[b][rr][cc], X + (size_t)(r0 + rr) * ldxy + xa + cc);
+                ps_cp_async8(&Bs[b][rr][cc], Y + (size_t)(r0 + rr) * ldxy + yb + cc);
+            } else { As[b][rr][cc] = 0.0; Bs[b][rr][cc] = 0.0; }
         }
+        ps_cp_commit();
+    };
+    __syncthreads();                                       // a previous call's last slab has been read
+    if (r_begin < r_end) prefetch(r_begin, 0);
+    int b = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += 32, b ^= 1) {
+        ps_cp_wait_all();
         __syncthreads();
+        if (r0 + 32 < r_end) prefetch(r0 + 32, b ^ 1);
 #pragma unroll
         for (int k0 = 0; k0 < 32; k0 += 4) {
-            const double a = As[k0 + fk][8 * si + fr];
-            const double b0 = Bs[k0 + fk][8 * sj + fr], b1 = Bs[k0 + fk][8 * sj + 8 + fr];
+            const double a = As[b][k0 + fk][8 * si + fr];
+            const double b0 = Bs[b][k0 + fk][8 * sj + fr], b1 = Bs[b][k0 + fk][8 * sj + 8 + fr];
             dmma_m8n8k4(c[0][0], c[0][1], a, b0);
             dmma_m8n8k4(c[1][0], c[1][1], a, b1);
         }
@@ -179,7 +285,10 @@ __device__ __forceinline__ void tile_xty_dmma(const double *__restrict__ X, cons
 // rows of the interior reach it),  gp_i = V_i^T y_i.  CTA = one output tile, the whole sum in a fixed order.
 __global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const double *__restrict__ S, int ld, const double *__restrict__ V,
                                                          const double *__restrict__ y, double *__restrict__ Dp, double *__restrict__ Ep, double *__restrict__ gp) {
-    __shared__ double As[32][PS_TLD], Bs[32][PS_TLD];
+    __shared__ double sg_sm[4 * 32 * PS_TLD];              // As[2] | Bs[2]; the gp branch uses the same bytes for its partial sums
+    double (*As)[32][PS_TLD] = reinterpret_cast<double (*)[32][PS_TLD]>(sg_sm);
+    double (*Bs)[32][PS_TLD] = reinterpret_cast<double (*)[32][PS_TLD]>(sg_sm + 2 * 32 * PS_TLD);
+    static_assert(8 * CR_MAXW <= 4 * 32 * PS_TLD, "gp partial sums must fit in the tile buffers");
     int i = 1;
     while (i + 1 < T.P && T.d[i + 1].tile0 <= (int)blockIdx.x) i++;
     const PartDesc &D = T.d[i];
@@ -211,15 +320,15 @@ __global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const doub
             __syncthreads();
             for (int e = tid; e < 1024; e += 256) {
                 const int rr = e >> 5, cc = e & 31;
-                const int c = r0 + rr, trow = D.m + 32 * b + cc;                 // Bs[rr][cc] = G(32 b + cc, c)
+                const int c = r0 + rr, trow = D.m + 32 * b + cc;                 // Bs[0][rr][cc] = G(32 b + cc, c)
                 const bool in = c < D.m;
-                As[rr][cc] = in ? __ldcg(Vp + (size_t)c * w + 32 * a + cc) : 0.0;
-                Bs[rr][cc] = (in && trow - c <= ld) ? __ldcg(S + (size_t)(D.r0 + c) * ld + D.r0 + trow) : 0.0;
+                As[0][rr][cc] = in ? __ldcg(Vp + (size_t)c * w + 32 * a + cc) : 0.0;
+                Bs[0][rr][cc] = (in && trow - c <= ld) ? __ldcg(S + (size_t)(D.r0 + c) * ld + D.r0 + trow) : 0.0;
             }
             __syncthreads();
 #pragma unroll 8
             for (int rr = 0; rr < 32; rr++) {
-                const double a0 = As[rr][ty], a1 = As[rr][ty + 16], b0 = Bs[rr][tx], b1 = Bs[rr][tx + 16];
+                const double a0 = As[0][rr][ty], a1 = As[0][rr][ty + 16], b0 = Bs[0][rr][tx], b1 = Bs[0][rr][tx + 16];
                 acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
             }
         }
@@ -229,14 +338,28 @@ __global__ void __launch_bounds__(256) spike_gram_kernel(PartTable T, const doub
             for (int v = 0; v < 2; v++) Ep[so + (size_t)(32 * a + ty + 16 * u) * w + 32 * b + tx + 16 * v] = acc[u][v];
         return;
     }
-    if (tile == nt * nt) {                               // ---- gp = V^T y (thread = column, fixed order over the rows)
+    if (tile == nt * nt) {                               // ---- gp = V^T y: warp v takes the rows r = v (mod 8), lane the columns t = lane (mod 32)
+        double (*gpart)[CR_MAXW] = reinterpret_cast<double (*)[CR_MAXW]>(sg_sm);   // (one thread per column walking all m rows is a chain of m exposed L2 loads)
         const double *yi = y + D.r0;
+        const int lane = tid & 31, wv = tid >> 5, ng = w / 32;
+        double acc[CR_MAXW / 32];
+#pragma unroll
+        for (int g = 0; g < CR_MAXW / 32; g++) acc[g] = 0.0;
+#pragma unroll 4
+        for (int r = wv; r < D.m; r += 8) {
+            const double yr = __ldcg(yi + r);
+            const double *vr = Vp + (size_t)r * w + lane;
+#pragma unroll
+            for (int g = 0; g < CR_MAXW / 32; g++) if (g < ng) acc[g] += __ldcg(vr + 32 * g) * yr;
+        }
+#pragma unroll
+        for (int g = 0; g < CR_MAXW / 32; g++) if (g < ng) gpart[wv][32 * g + lane] = acc[g];
+        __syncthreads();
         for (int t = tid; t < w; t += 256) {
-            double s0 = 0.0, s1 = 0.0;
-            int r = 0;
-            for (; r + 1 < D.m; r += 2) { s0 += __ldcg(Vp + (size_t)r * w + t) * __ldcg(yi + r); s1 += __ldcg(Vp + (size_t)(r + 1) * w + t) * __ldcg(yi + r + 1); }
-            if (r < D.m) s0 += __ldcg(Vp + (size_t)r * w + t) * __ldcg(yi + r);
-            gp[(size_t)D.sep * w + t] = s0 + s1;
+            double sum = 0.0;
+#pragma unroll
+            for (int v = 0; v < 8; v++) sum += gpart[v][t];
+            gp[(size_t)D.sep * w + t] = sum;
         }
     }
 }
@@ -382,7 +505,6 @@ __global__ void __launch_bounds__(32 * PS_INV_WARPS) block_inverse_kernel(CrPlan
 }
 
 // Fa_j = L_j^-1 C_{j-s}^T (side 0), Fb_j = L_j^-1 C_j (side 1), PS_NCOL columns per CTA; blockIdx = ((t * 2 + side) * (w / PS_NCOL) + group)
-#define CR_MAXW 384
 __global__ void __launch_bounds__(PS_THREADS) block_spike_kernel(CrPlan C, int s, int cnt) {
     __shared__ double win[CR_MAXW][PS_NCOL];
     __shared__ double Li[32][33];
@@ -434,7 +556,7 @@ __global__ void __launch_bounds__(PS_THREADS) block_spike_kernel(CrPlan C, int s
 
 // the blocks that stay at this level: t = 2 s - 1 + 2 s u. blockIdx = u * (2 nt^2 + 1) + tile
 __global__ void __launch_bounds__(256) block_gram_kernel(CrPlan C, int s, int n_keep) {
-    __shared__ double As[32][PS_TLD], Bs[32][PS_TLD];
+    __shared__ double As[2][32][PS_TLD], Bs[2][32][PS_TLD];
     const int w = C.w, nt = w / 32, per = 2 * nt * nt + 1;
     const int u = blockIdx.x / per;
     int tile = blockIdx.x - u * per;
@@ -471,9 +593,11 @@ __global__ void __launch_bounds__(256) block_gram_kernel(CrPlan C, int s, int n_
     for (int c = tid; c < w; c += 256) {                    // g_t
         double s0 = 0.0, s1 = 0.0;
         const double *F = C.Fb + jl * ww, *yv = C.yy + (size_t)jl * w;
+#pragma unroll 8
         for (int r = 0; r < w; r++) s0 += __ldcg(F + (size_t)r * w + c) * __ldcg(yv + r);
         if (has_r) {
             F = C.Fa + jr * ww; yv = C.yy + (size_t)jr * w;
+#pragma unroll 8
             for (int r = 0; r < w; r++) s1 += __ldcg(F + (size_t)r * w + c) * __ldcg(yv + r);
         }
         C.gg[(size_t)t * w + c] -= s0 + s1;

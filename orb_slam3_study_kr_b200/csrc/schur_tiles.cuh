@@ -183,6 +183,7 @@ struct TileArgs {
     double *hpp_diag;             // optional [6 n_free]: diagonal-only pass of computeLambdaInit
     unsigned *work;               // [4] next item / warps that ran out of items, per kernel (zero at launch; the last warp out resets them)
     const LmDev *lm = nullptr;    // chained mode: nothing to do once the LM loop has ended
+    int item_begin = 0, item_end = -1;   // pair_tile_mma_kernel: the items of this launch (-1: all); a multi-GPU trial launches the rows chunk by chunk
 };
 
 BA_DEV void cp_async16(void *smem_dst, const void *gsrc) {
@@ -482,9 +483,9 @@ __global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(Tile
     if (lm_done(P.lm)) return;
     for (;;) {
         int it = 0;
-        if (lane == 0) it = (int)atomicAdd(P.work, 1u);
+        if (lane == 0) it = P.item_begin + (int)atomicAdd(P.work, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= P.n_items) break;
+        if (it >= (P.item_end < 0 ? P.n_items : P.item_end)) break;
         const TileItem I = P.items[it];
         const bool dt = I.ta == I.tb;
         const bool multi = I.nit > 1;
