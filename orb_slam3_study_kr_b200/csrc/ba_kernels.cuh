@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_kernel(BaDev D, const dou
 #define ST_THREADS 256
 #ifndef ST_MINB
 #define ST_MINB 2                          // resident CTAs per SM asked of the compiler for stage / update_packed
-#endif
+#endif  // ST_MINB
 #define ST_WARPS (ST_THREADS / 32)
 
 struct UpdateOut {

@@ -930,7 +930,9 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                 CK(cudaMemsetAsync(ovf, 0, sizeof(int), sp));
                 tile_plan_kernel<false><<<g, 256, 0, sp>>>(Ne, ctx->d_lm_ptr.as<int>(), ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(),
                                                            ctx->d_tile_pos.as<int>(), tbw1, npairs, blkcnt, nullptr, nullptr, nullptr, nullptr, ovf);
-                tile_item_count_kernel<<<grid_for(nblk + 1, 256), 256, 0, sp>>>(nblk + 1, blkcnt, itemcnt);
+                // records per work item: long items on big maps (fewer partial sums through memory), shorter ones where the items would not fill the device
+                const unsigned chunk = (Ne >= 1000000) ? TP_CHUNK : TP_CHUNK / 2;
+                tile_item_count_kernel<<<grid_for(nblk + 1, 256), 256, 0, sp>>>(nblk + 1, blkcnt, itemcnt, chunk);
                 size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
                 CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, npairs, pairoff, (int)(ne + 1), sp));
                 CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, blkcnt, blkoff, nblk + 1, sp));
@@ -967,7 +969,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
                         CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, tmp, ctx->d_pk_keys.as<unsigned>(), ctx->d_pk_keys2.as<unsigned>(),
                                                            ctx->d_tp_idx.as<unsigned>(), ctx->d_tp_idx2.as<unsigned>(), (int)nrec, 0, end_bit, sp));
                         tile_gather_kernel<<<grid_for((int64_t)nrec, 256), 256, 0, sp>>>((unsigned)nrec, ctx->d_tp_idx2.as<unsigned>(), ctx->d_tp_raw.as<TileRec>(), ctx->d_tp_recs.as<TileRec>());
-                        tile_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, sp>>>(nblk, tbw1, ctx->d_tile_of_pos.as<int>(), blkoff, blkcnt, itemoff, ctx->d_items.as<TileItem>());
+                        tile_item_fill_kernel<<<grid_for(nblk, 256), 256, 0, sp>>>(nblk, tbw1, ctx->d_tile_of_pos.as<int>(), blkoff, blkcnt, itemoff, ctx->d_items.as<TileItem>(), chunk);
                         CK(cudaGetLastError());
                     }
                     CK(ctx->d_part.ensure(sizeof(double) * TP_PART * (size_t)std::max(1, ctx->n_items)));

@@ -26,7 +26,7 @@
 
 #define TP_T 4
 #ifndef TP_CHUNK
-#define TP_CHUNK 128                       // records per work item
+#define TP_CHUNK 256                       // most records per work item (the plan uses 128 for small maps: more items, shorter chains)
 #endif
 #define TP_THREADS 128
 #define TP_WARPS (TP_THREADS / 32)
@@ -148,13 +148,13 @@ __global__ void tile_gather_kernel(unsigned n, const unsigned *__restrict__ idx,
     d[0] = s[0]; d[1] = s[1];
 }
 
-__global__ void tile_item_count_kernel(int nblk, const unsigned *__restrict__ blk_cnt, unsigned *__restrict__ item_cnt) {
+__global__ void tile_item_count_kernel(int nblk, const unsigned *__restrict__ blk_cnt, unsigned *__restrict__ item_cnt, unsigned chunk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nblk) item_cnt[i] = (blk_cnt[i] + TP_CHUNK - 1) / TP_CHUNK;
+    if (i < nblk) item_cnt[i] = (blk_cnt[i] + chunk - 1) / chunk;
 }
 
 __global__ void tile_item_fill_kernel(int nblk, int tbw1, const int *__restrict__ tile_of_pos, const unsigned *__restrict__ blk_off, const unsigned *__restrict__ blk_cnt,
-                                      const unsigned *__restrict__ item_off, TileItem *__restrict__ items) {
+                                      const unsigned *__restrict__ item_off, TileItem *__restrict__ items, unsigned chunk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk) return;
     const unsigned cnt = blk_cnt[i];
@@ -162,9 +162,9 @@ __global__ void tile_item_fill_kernel(int nblk, int tbw1, const int *__restrict_
     const int tp = i / tbw1, ta = tile_of_pos[tp], tb = ta + (i - tp * tbw1);
     const unsigned off = blk_off[i];
     unsigned io = item_off[i];
-    const int nit = (int)((cnt + TP_CHUNK - 1) / TP_CHUNK);
-    for (unsigned c = 0; c < cnt; c += TP_CHUNK) {
-        TileItem I; I.ta = ta; I.tb = tb; I.begin = (int)(off + c); I.end = (int)(off + min(cnt, c + TP_CHUNK));
+    const int nit = (int)((cnt + chunk - 1) / chunk);
+    for (unsigned c = 0; c < cnt; c += chunk) {
+        TileItem I; I.ta = ta; I.tb = tb; I.begin = (int)(off + c); I.end = (int)(off + min(cnt, c + chunk));
         I.first = (int)item_off[i]; I.nit = nit;
         items[io++] = I;
     }
