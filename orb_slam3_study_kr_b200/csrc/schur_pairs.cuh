@@ -7,7 +7,7 @@
 //   stage_kernel / stage_wide_kernel   landmark-major (lane = observation). Linearise, reduce the landmark's Hll / bl,
 //       factor Hll + lambda I = L L^T (3x3 Cholesky, in registers) and write per observation
 //         Z  = W L^-T = [P^T Y; Y]         (6x3; W = rho1 w B^T A is the Hpl block; stored as Y (3x3) and X_l, P = -[X_l]x)
-//         Dr = [ w M^T M (6) | M^T g (3) | Y L^-1 bl (3) ], B = M [-[X_l]x | I]   -> the per-camera sums (Hpp, bp, bs)
+//         Dr = [ w M^T M (6) | M^T g (3) | Y L^-1 bl (3) | X_l (3) ], B = M [-[X_l]x | I]   -> the per-camera sums (Hpp, bp, bs)
 //       and per landmark the factor L, L^-1 bl and bl (update_z_kernel back-substitutes from these, no second linearisation).
 //   pair_kernel    camera-pair-major. At upload the device lists, for every upper block (a, b) of the reduced system,
 //       the observation pairs (e_a, e_b) of the landmarks both cameras see, sorted by block (pair_plan_*). A warp takes
@@ -21,7 +21,8 @@
 #include "ba_kernels.cuh"
 
 #define ZR_STRIDE 12                       // Y (9) | X_l (3): 96-byte records = three 32-byte sectors, one 256-bit access each
-#define DR_STRIDE 12                       // [w M^T M (6) | M^T g (3) | Y L^-1 b_l (3)], three sectors (X_l is read from the Z record)
+#define DR_STRIDE 16                       // 15 used: [w M^T M (6) | M^T g (3) | Y L^-1 b_l (3) | X_l (3)]: 128 bytes = exactly two 64-byte L2 fetches per gather
+                                           // (a 96-byte record + the X_l sector of the Z record costs 128 + 64 bytes of DRAM reads at the L2's 64-byte fetch granularity)
 #define LM_STRIDE 12
 #ifndef PK_CHUNK
 #define PK_CHUNK 512                       // entries per work item (per-item reductions vs the working set of the chunks in flight)
@@ -186,6 +187,7 @@ BA_DEV void lane_emit(const LaneEdge &E, const LmFactor &F, int64_t e, double *_
     stg256(dout, n00, n01, n02, n11);
     stg256(dout + 4, n12, n22, g0, g1);
     stg256(dout + 8, g2, q[0], q[1], q[2]);
+    stg256(dout + 12, X0, X1, X2, 0.0);
 }
 
 struct StageArgs {
@@ -415,12 +417,11 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
                 const int2 en = __ldg(P.entries + i);
                 if (en.x != en.y) continue;
                 const double *pd = P.Dr + DR_STRIDE * (size_t)en.x;
-                double v[DR_STRIDE], zx[4];
+                double v[DR_STRIDE];
 #pragma unroll
                 for (int q = 0; q < DR_STRIDE / 4; q++) ldg256(pd + 4 * q, v + 4 * q);
-                ldg256(P.Z + ZR_STRIDE * (size_t)en.x + 8, zx);
-                // v = N (6) | m (3) | q (3), X from the Z record.  w B^T B = [P | I]^T N [P | I] with P = -[X]x; T = N P, TL = P^T T
-                const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = zx[1], y = zx[2], z = zx[3];
+                // v = N (6) | m (3) | q (3) | X (3).  w B^T B = [P | I]^T N [P | I] with P = -[X]x; T = N P, TL = P^T T
+                const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = v[12], y = v[13], z = v[14];
                 const double t00 = -z * n01 + y * n02, t01 = z * n00 - x * n02, t02 = -y * n00 + x * n01;
                 const double t10 = -z * n11 + y * n12, t11 = z * n01 - x * n12, t12 = -y * n01 + x * n11;
                 const double t20 = -z * n12 + y * n22, t21 = z * n02 - x * n22, t22 = -y * n02 + x * n12;

@@ -231,20 +231,19 @@ BA_DEV void tile_accumulate(const double *__restrict__ pa, const double *__restr
     }
 }
 
-// d (33) += the Hpp / b_p / b_s terms of observation e:  Dr = [N (6) | m (3) | q (3)], X_l from the Z record.
+// d (33) += the Hpp / b_p / b_s terms of observation e:  Dr = [N (6) | m (3) | q (3) | X_l (3)]
 //   w B^T B = [P | I]^T N [P | I],  B^T g = [P^T m; m],  -Z L^-1 b_l = -[P^T q; q]
 BA_DEV void tile_diag_add(const double *v, double *d);
-BA_DEV void tile_diag_accumulate(const double *__restrict__ Dr, const double *__restrict__ Z, int e, double *d) {
+BA_DEV void tile_diag_accumulate(const double *__restrict__ Dr, int e, double *d) {
     const double *pd = Dr + DR_STRIDE * (size_t)e;
-    double v[DR_STRIDE + 4];
+    double v[DR_STRIDE];
 #pragma unroll
     for (int q = 0; q < DR_STRIDE / 4; q++) ldg256(pd + 4 * q, v + 4 * q);
-    ldg256(Z + ZR_STRIDE * (size_t)e + 8, v + DR_STRIDE);
     tile_diag_add(v, d);
 }
-// v = [N (6) | m (3) | q (3) | y8 X_l (4)]
+// v = [N (6) | m (3) | q (3) | X_l (3) | -]
 BA_DEV void tile_diag_add(const double *v, double *d) {
-    const double *zx = v + DR_STRIDE;
+    const double *zx = v + DR_STRIDE - 5;                      // zx[1..3] = X_l
     const double n00 = v[0], n01 = v[1], n02 = v[2], n11 = v[3], n12 = v[4], n22 = v[5], x = zx[1], y = zx[2], z = zx[3];
     const double t00 = -z * n01 + y * n02, t01 = z * n00 - x * n02, t02 = -y * n00 + x * n01;
     const double t10 = -z * n11 + y * n12, t11 = z * n01 - x * n12, t12 = -y * n01 + x * n11;
@@ -355,7 +354,7 @@ __global__ void __launch_bounds__(TP_THREADS, TP_MINB) pair_tile_kernel(TileArgs
             for (int i = 0; i < 33; i++) d[i] = 0.0;
             for (int r = lane >> 2; r < nr; r += 8) {
                 const int ea = srec[8 * r + dc], eb = srec[8 * r + 4 + dc];
-                if (ea >= 0 && ea == eb) tile_diag_accumulate(P.Dr, P.Z, ea, d);          // the (G, G) record of a group holds each observation once
+                if (ea >= 0 && ea == eb) tile_diag_accumulate(P.Dr, ea, d);          // the (G, G) record of a group holds each observation once
             }
 #pragma unroll
             for (int i = 0; i < 33; i++) {
@@ -527,6 +526,8 @@ __global__ void __launch_bounds__(TP_THREADS, TM_MINB) pair_tile_mma_kernel(Tile
         };
         // group g: expand `cur` (fetched two groups ago), start the fetch of group g + 2 into `fill`, 27 / 18 DMMAs
         int idx_q = -1;                                        // index of my slot in group g + 2 (loaded one group earlier)
+        // (skipping the DMMAs of all-zero 8-row operand blocks -- warp-uniform branches on a ballot of the group's slots -- was measured:
+        // 3.84 ms instead of 2.35 ms per launch on config 5; the predicated chain no longer overlaps fragment loads and tensor instructions)
         auto group = [&](int g, const double *cur, double *fill) {
             double *buf = E + (g & 1) * TM_BUF + st_off;
             {   // rows 7 i .. 7 i + 5 of my side, columns 3 rec .. 3 rec + 2;  [X]x y = (-z y1 + y y2, z y0 - x y2, -y y0 + x y1) per column y of Y
@@ -648,9 +649,9 @@ __global__ void __launch_bounds__(TP_THREADS, 3) tile_diag_kernel(TileArgs P) {
         int e0 = obs_of(lane >> 2), e1 = obs_of((lane >> 2) + 8);
         for (int r = lane >> 2; r < nr; r += 16) {
             const int n0 = obs_of(r + 16), n1 = obs_of(r + 24);
-            double v0[DR_STRIDE + 4], v1[DR_STRIDE + 4];
-            if (e0 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e0; ldg256(pd, v0); ldg256(pd + 4, v0 + 4); ldg256(pd + 8, v0 + 8); ldg256(P.Z + ZR_STRIDE * (size_t)e0 + 8, v0 + 12); }
-            if (e1 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e1; ldg256(pd, v1); ldg256(pd + 4, v1 + 4); ldg256(pd + 8, v1 + 8); ldg256(P.Z + ZR_STRIDE * (size_t)e1 + 8, v1 + 12); }
+            double v0[DR_STRIDE], v1[DR_STRIDE];
+            if (e0 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e0; ldg256(pd, v0); ldg256(pd + 4, v0 + 4); ldg256(pd + 8, v0 + 8); ldg256(pd + 12, v0 + 12); }
+            if (e1 >= 0) { const double *pd = P.Dr + DR_STRIDE * (size_t)e1; ldg256(pd, v1); ldg256(pd + 4, v1 + 4); ldg256(pd + 8, v1 + 8); ldg256(pd + 12, v1 + 12); }
             if (e0 >= 0) tile_diag_add(v0, d);
             if (e1 >= 0) tile_diag_add(v1, d);
             e0 = n0; e1 = n1;
