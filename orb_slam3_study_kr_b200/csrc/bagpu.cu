@@ -94,9 +94,10 @@ enum { EV_BUILD = 0, EV_LINSOLVE = 1, EV_UPDATE = 2, EV_KINDS = 3 };
 namespace {
 // Host-side planning runs over millions of observations per upload: split the landmark / observation ranges over a few
 // threads (the calling SLAM thread blocks in bagpu_upload anyway). fn(thread, begin, end).
+constexpr int kPlanThreads = 8;
 template <class F>
 void parallel_ranges(int64_t n, int64_t min_chunk, F fn) {
-    static const int hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    static const int hw = std::max(1u, std::min((unsigned)kPlanThreads, std::thread::hardware_concurrency()));
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(hw, n / std::max<int64_t>(1, min_chunk)));
     if (nt <= 1) { fn(0, (int64_t)0, n); return; }
     std::vector<std::thread> th;
@@ -105,7 +106,6 @@ void parallel_ranges(int64_t n, int64_t min_chunk, F fn) {
     fn(0, (int64_t)0, n / nt);
     for (auto &x : th) x.join();
 }
-constexpr int kPlanThreads = 8;
 
 }  // namespace
 
@@ -218,7 +218,8 @@ struct bagpu_ctx {
     size_t s_elems = 0, scratch_elems = 0; int chol_grid = 1; int chol_maxr = 0; int band_blocks = 0;
     DevBuf d_xp, d_parts, d_status, d_chi2, d_depth, d_out_chi2, d_out_u8a, d_out_u8b, d_fail, d_count;
     PinBuf h_status, h_stage;
-    DevBuf d_lm, d_lm_trace; PinBuf h_lm;      // chained mode: LM state and per-iteration records on the device
+    DevBuf d_lm, d_lm_trace; PinBuf h_lm;
+    DevBuf d_lastrow; PinBuf h_lastrow, h_lmptr; cudaEvent_t ev_lastrow = nullptr;   // upload: envelope computed on the device while the host checks the order      // chained mode: LM state and per-iteration records on the device
     std::vector<int> h_hidx;
     std::vector<int> h_colend, h_ce1, h_ce2, h_ceM;      // envelope arrays: kept alive, copied on the main stream without a sync
     double *pose_cur = nullptr, *pose_trial = nullptr, *pt_cur = nullptr, *pt_trial = nullptr;
@@ -386,6 +387,19 @@ __global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, fl
     if (i < n) o[i] = baf_atan2f(y[i], x[i]);
 }
 
+// envelope of the reduced system from the landmark structure: lastrow[h] = largest free index among the poses that share a landmark with
+// free pose h (observations landmark-major, pose-ascending: the partner with the largest index is the last free observation of the run)
+__global__ void lastrow_kernel(int64_t n_obs, const int *__restrict__ o_pose, const int *__restrict__ o_point, const int *__restrict__ hidx, int *lastrow) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_obs) return;
+    const int h = hidx[o_pose[e]];
+    if (h < 0) return;
+    const int j = o_point[e];
+    int mx = h;
+    for (int64_t e2 = e + 1; e2 < n_obs && o_point[e2] == j; e2++) mx = max(mx, hidx[o_pose[e2]]);
+    atomicMax(lastrow + h, mx);
+}
+
 inline int grid_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
 BaDev make_dev(bagpu_ctx *ctx, double delta_mono, double delta_stereo) {
@@ -407,23 +421,46 @@ int validate_problem(bagpu_ctx *ctx, const bagpu_problem *p) {
         !p->obs_kind || !p->obs_flags || !p->obs_u || !p->obs_v || !p->obs_inv_sigma2)
         return fail(ctx, BAGPU_ERR_ARG, "NULL array in problem");
     if (p->n_cameras > 255 || p->n_rigs > 254) return fail(ctx, BAGPU_ERR_ARG, "too many cameras/rigs");
-    // one pass over the observations, split over a few host threads (2 M observations: 0.5 ms instead of 3)
+    return BAGPU_OK;
+}
+// the per-observation checks: one pass, split over a few host threads (2 M observations: 0.5 ms instead of 3); bagpu_upload runs it
+// while the observation arrays are already crossing PCIe (the bytes of a rejected problem are never used)
+// (the same pass checks the order -- landmark-major, pose-ascending inside a landmark -- and notes where each landmark's run starts)
+int validate_observations(bagpu_ctx *ctx, const bagpu_problem *p, std::vector<int> &lm_ptr, bool &sorted_out) {
     std::atomic<int> any_stereo_a{0};
+    std::atomic<bool> sorted_a{true};
     std::atomic<long long> bad_e{-1};
     std::atomic<int> bad_why{0};
+    const int n_poses = p->n_poses, n_points = p->n_points, n_cameras = p->n_cameras, n_rigs = p->n_rigs;
+    const int *op = p->obs_pose, *opt = p->obs_point; const int16_t *oc = p->obs_cam, *org = p->obs_rig; const uint8_t *ok = p->obs_kind;
     parallel_ranges(p->n_obs, 1 << 16, [&](int, int64_t e0, int64_t e1) {
-        bool st = false;
+        // branch-free first (the compiler vectorises these reductions); the exact culprit is looked up only when something is wrong
+        unsigned bad = 0u, st = 0u, uns = 0u;
         for (int64_t e = e0; e < e1; e++) {
-            int why = 0;
-            if (p->obs_pose[e] < 0 || p->obs_pose[e] >= p->n_poses || p->obs_point[e] < 0 || p->obs_point[e] >= p->n_points) why = 1;
-            else if (p->obs_cam[e] < 0 || p->obs_cam[e] >= p->n_cameras) why = 2;
-            else if (p->obs_kind[e] > 2) why = 3;
-            else if (p->obs_kind[e] == BAGPU_EDGE_BODY && (p->obs_rig[e] < 0 || p->obs_rig[e] >= p->n_rigs)) why = 4;
-            if (why) { long long exp = -1; if (bad_e.compare_exchange_strong(exp, (long long)e)) bad_why.store(why); return; }
-            if (p->obs_kind[e] == BAGPU_EDGE_STEREO) st = true;
+            bad |= (unsigned)((unsigned)op[e] >= (unsigned)n_poses) | (unsigned)((unsigned)opt[e] >= (unsigned)n_points) |
+                   (unsigned)((unsigned)(int)oc[e] >= (unsigned)n_cameras) | (unsigned)(ok[e] > 2) |
+                   (unsigned)((ok[e] == BAGPU_EDGE_BODY) & ((unsigned)(int)org[e] >= (unsigned)n_rigs));
+            st |= (unsigned)(ok[e] == BAGPU_EDGE_STEREO);
         }
+        if (bad) {
+            for (int64_t e = e0; e < e1; e++) {
+                int why = 0;
+                if (op[e] < 0 || op[e] >= n_poses || opt[e] < 0 || opt[e] >= n_points) why = 1;
+                else if (oc[e] < 0 || oc[e] >= n_cameras) why = 2;
+                else if (ok[e] > 2) why = 3;
+                else if (ok[e] == BAGPU_EDGE_BODY && (org[e] < 0 || org[e] >= n_rigs)) why = 4;
+                if (why) { long long exp = -1; if (bad_e.compare_exchange_strong(exp, (long long)e)) bad_why.store(why); return; }
+            }
+        }
+        for (int64_t e = std::max<int64_t>(e0, 1); e < e1; e++)
+            uns |= (unsigned)(opt[e - 1] > opt[e]) | (unsigned)((opt[e - 1] == opt[e]) & (op[e - 1] > op[e]));
+        if (e0 == 0) lm_ptr[(size_t)opt[0]] = 0;
+        for (int64_t e = std::max<int64_t>(e0, 1); e < e1; e++)
+            if (opt[e - 1] != opt[e]) lm_ptr[(size_t)opt[e]] = (int)e;           // only meaningful (and only used) when the order holds
+        if (uns) sorted_a.store(false, std::memory_order_relaxed);
         if (st) any_stereo_a.store(1, std::memory_order_relaxed);
     });
+    sorted_out = sorted_a.load();
     if (bad_e.load() >= 0) {
         static const char *msg[] = {"", "vertex index out of range", "camera index out of range", "bad kind", "rig index out of range"};
         return fail(ctx, BAGPU_ERR_ARG, "observation %lld: %s", bad_e.load(), msg[bad_why.load()]);
@@ -484,13 +521,14 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         for (auto &e : ctx->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev_phase[i]);
+    cudaEventCreateWithFlags(&ctx->ev_lastrow, cudaEventDisableTiming);
     {
         // Load every kernel now. With CUDA's lazy module loading the FIRST launch of a kernel may synchronise the context; a
         // launch that does so while the Cholesky clusters spin on pair_kernel's counters (pair_kernel not yet enqueued) would
         // block the host until the watchdog fires.
         cudaFuncAttributes fa;
         const void *fns[] = {(const void *)compose_meta_kernel, (const void *)gather_perm_kernel<int>, (const void *)gather_perm_kernel<double>,
-                             (const void *)gather_perm_kernel<uint32_t>, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel, (const void *)row_order_kernel,
+                             (const void *)gather_perm_kernel<uint32_t>, (const void *)lastrow_kernel, (const void *)tw_merge_kernel, (const void *)tw_scatter_kernel, (const void *)row_order_kernel,
                              (const void *)atan2f_test_kernel, (const void *)fp64_dfma_probe_kernel, (const void *)fp64_dmma_probe_kernel, (const void *)build_kernel, (const void *)update_kernel, (const void *)update_packed_kernel, (const void *)update_z_kernel,
                              (const void *)gate_kernel, (const void *)count_active_kernel, (const void *)pose_update_kernel, (const void *)reduce_partials_kernel, (const void *)finish_trial_kernel,
                              (const void *)scatter_perm_kernel<double>, (const void *)scatter_perm_kernel<uint8_t>, (const void *)level_from_meta_kernel,
@@ -602,6 +640,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev_phase[0], st));
     ctx->have_problem = false;
+    struct DrainOnError { cudaStream_t s; bool armed = true; ~DrainOnError() { if (armed) cudaStreamSynchronize(s); } } drain{st};   // an early return must not leave copies of the caller's arrays in flight
     const int Nt = p->n_poses, Np = p->n_points;
     const int64_t Ne = p->n_obs;
     ctx->n_poses = Nt; ctx->n_points = Np; ctx->n_obs = Ne; ctx->n_cams = p->n_cameras; ctx->n_rigs = p->n_rigs;
@@ -612,21 +651,52 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     const double tw0 = wall();
     double lap_t = tw0; std::string laps;
     auto lap = [&](const char *name) { if (dbg_t) { const double t = wall(); char buf[64]; snprintf(buf, sizeof(buf), " %s %.2f", name, t - lap_t); laps += buf; lap_t = t; } };
-    // --- order: landmark-major, pose-ascending inside a landmark, insertion order preserved among equals
-    // one pass: order check AND (for the sorted case) the run boundaries lm_ptr[j] = first observation of landmark j
-    std::atomic<bool> sorted_a{true};
+    // --- the observation arrays go up FIRST, straight into their final places, as if they were already in the order the kernels want
+    // (Optimizer.cc's per-MapPoint loops produce it): PCIe is the long pole of an upload, and the host's own passes (order check, CSR
+    // pointers, envelope) run while the bytes cross. If the check below finds another order, the arrays are uploaded again through the
+    // staging buffer and gathered (the speculative copies are overwritten: same stream).
+    const size_t ne = (size_t)Ne;
+    CK(ctx->d_o_pose.ensure(4 * ne)); CK(ctx->d_o_point.ensure(4 * ne)); CK(ctx->d_o_meta.ensure(4 * ne));
+    CK(ctx->d_o_u.ensure(8 * ne)); CK(ctx->d_o_v.ensure(8 * ne)); CK(ctx->d_o_w.ensure(8 * ne)); CK(ctx->d_o_ur.ensure(8 * ne));
+    CK(ctx->d_raw8a.ensure(ne)); CK(ctx->d_raw8b.ensure(ne)); CK(ctx->d_raw16a.ensure(2 * ne)); CK(ctx->d_raw16b.ensure(2 * ne));
+    CK(ctx->d_chi2.ensure(8 * ne)); CK(ctx->d_depth.ensure(ne));
+    cudaStream_t sp = ctx->stream_chol;
+    ctx->h_hidx.assign(Nt, -1);
+    int nf = 0;
+    for (int i = 0; i < Nt; i++) if (!p->pose_fixed[i]) ctx->h_hidx[i] = nf++;
+    ctx->n_free = nf;
+    CK(ctx->d_hidx.ensure(sizeof(int) * (size_t)Nt));
+    CK(cudaMemcpyAsync(ctx->d_hidx.p, ctx->h_hidx.data(), sizeof(int) * (size_t)Nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_pose.p, p->obs_pose, 4 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_point.p, p->obs_point, 4 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev_fork, st));                 // (sorted case) the plan stream needs only the index arrays
+    {   // ... and so does the envelope: computed on the plan stream now, read by the host after its own passes
+        CK(ctx->d_lastrow.ensure(sizeof(int) * (size_t)std::max(1, nf))); CK(ctx->h_lastrow.ensure(sizeof(int) * (size_t)std::max(1, nf)));
+        CK(cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
+        CK(cudaMemsetAsync(ctx->d_lastrow.p, 0xff, sizeof(int) * (size_t)std::max(1, nf), sp));
+        lastrow_kernel<<<grid_for(Ne, 256), 256, 0, sp>>>(Ne, ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(), ctx->d_lastrow.as<int>());
+        // every rank must lay the reduced camera system out identically: the envelope is the union over the shards
+        if (ctx->world > 1 && nf > 0) CKN(g_nccl.AllReduce(ctx->d_lastrow.p, ctx->d_lastrow.p, (size_t)nf, ncclInt32, ncclMax, ctx->comm, sp));
+        CK(cudaMemcpyAsync(ctx->h_lastrow.p, ctx->d_lastrow.p, sizeof(int) * (size_t)std::max(1, nf), cudaMemcpyDeviceToHost, sp));
+        CK(cudaEventRecord(ctx->ev_lastrow, sp));
+    }
+    CK(cudaMemcpyAsync(ctx->d_raw8a.p, p->obs_kind, ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw8b.p, p->obs_flags, ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw16a.p, p->obs_cam, 2 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_raw16b.p, p->obs_rig, 2 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_u.p, p->obs_u, 8 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_v.p, p->obs_v, 8 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_o_w.p, p->obs_inv_sigma2, 8 * ne, cudaMemcpyHostToDevice, st));
+    if (p->obs_ur) CK(cudaMemcpyAsync(ctx->d_o_ur.p, p->obs_ur, 8 * ne, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * ne, st));
+    lap("obs-enqueue");
+    // --- validation + order: landmark-major, pose-ascending inside a landmark, insertion order preserved among equals. One pass checks
+    // every observation AND the order AND (for the sorted case) notes the run boundaries lm_ptr[j] = first observation of landmark j
     std::vector<int> lm_ptr((size_t)Np + 1, -1);
-    parallel_ranges(Ne, 1 << 16, [&](int, int64_t e0, int64_t e1) {
-        for (int64_t e = e0; e < e1; e++) {
-            const int bpt = p->obs_point[e];
-            if (e == 0) { lm_ptr[(size_t)bpt] = 0; continue; }
-            const int apt = p->obs_point[e - 1];
-            if (apt != bpt) lm_ptr[(size_t)bpt] = (int)e;
-            if (apt > bpt || (apt == bpt && p->obs_pose[e - 1] > p->obs_pose[e])) { sorted_a.store(false, std::memory_order_relaxed); break; }
-        }
-    });
-    const bool sorted = sorted_a.load();
-    lap("check");
+    bool sorted = true;
+    rc = validate_observations(ctx, p, lm_ptr, sorted);
+    if (rc) return rc;
+    lap("validate+check");
     if (sorted) {
         // landmarks without observations inherit the next one
         lm_ptr[(size_t)Np] = (int)Ne;
@@ -656,15 +726,37 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     std::vector<int2> tasks;
     std::vector<int> wide_list;
     struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } tasks_thread;
+    // (a fixed number of segments, each packed greedily on its own thread: the partition -- and with it every summation order -- depends
+    // on the map only, not on the host's core count)
+    constexpr int kTaskSegs = 16;
     tasks_thread.t = std::thread([&tasks, &wide_list, &lm_ptr, Np] {
-        int tb = -1, tobs = 0;
-        tasks.reserve((size_t)Np / 2 + 16);
-        for (int j = 0; j <= Np; j++) {
-            const int k = (j < Np) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
-            const bool brk = j == Np || k > 32;
-            if (tb >= 0 && (brk || tobs + k > 32)) { tasks.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
-            if (!brk) { if (tb < 0) tb = j; tobs += k; }
-            else if (j < Np) wide_list.push_back(j);
+        std::vector<int2> seg_tasks[kTaskSegs];
+        std::vector<int> seg_wide[kTaskSegs];
+        auto pack = [&](int sgm) {
+            const int j0 = (int)((long long)Np * sgm / kTaskSegs), j1 = (int)((long long)Np * (sgm + 1) / kTaskSegs);
+            std::vector<int2> &T = seg_tasks[sgm];
+            T.reserve((size_t)(j1 - j0) / 2 + 16);
+            int tb = -1, tobs = 0;
+            for (int j = j0; j <= j1; j++) {
+                const int k = (j < j1) ? lm_ptr[j + 1] - lm_ptr[j] : 0;
+                const bool brk = j == j1 || k > 32;
+                if (tb >= 0 && (brk || tobs + k > 32)) { T.push_back(make_int2(tb, j)); tb = -1; tobs = 0; }
+                if (!brk) { if (tb < 0) tb = j; tobs += k; }
+                else if (j < j1) seg_wide[sgm].push_back(j);
+            }
+        };
+        if (Np >= (1 << 16)) {
+            std::vector<std::thread> th;
+            for (int sgm = 1; sgm < kTaskSegs; sgm++) th.emplace_back(pack, sgm);
+            pack(0);
+            for (auto &x : th) x.join();
+        } else for (int sgm = 0; sgm < kTaskSegs; sgm++) pack(sgm);
+        size_t nt = 0, nw = 0;
+        for (int sgm = 0; sgm < kTaskSegs; sgm++) { nt += seg_tasks[sgm].size(); nw += seg_wide[sgm].size(); }
+        tasks.reserve(nt); wide_list.reserve(nw);
+        for (int sgm = 0; sgm < kTaskSegs; sgm++) {
+            tasks.insert(tasks.end(), seg_tasks[sgm].begin(), seg_tasks[sgm].end());
+            wide_list.insert(wide_list.end(), seg_wide[sgm].begin(), seg_wide[sgm].end());
         }
     });
 
@@ -674,15 +766,10 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     for (int i = 0; i < Nt; i++) normalize_qt(p->pose_qt + 7 * (size_t)i, hp + 7 * (size_t)i);
     double *hr = hp + 7 * (size_t)Nt;
     for (int i = 0; i < p->n_rigs; i++) normalize_qt(p->rigs[i].qt, hr + 7 * (size_t)i);
-    ctx->h_hidx.assign(Nt, -1);
-    int nf = 0;
-    for (int i = 0; i < Nt; i++) if (!p->pose_fixed[i]) ctx->h_hidx[i] = nf++;
-    ctx->n_free = nf;
 
     CK(ctx->d_pose_a.ensure(sizeof(double) * 7 * (size_t)Nt)); CK(ctx->d_pose_b.ensure(sizeof(double) * 7 * (size_t)Nt));
     CK(ctx->d_pose_init.ensure(sizeof(double) * 7 * (size_t)Nt));
     CK(ctx->d_pt_a.ensure(sizeof(double) * 3 * (size_t)Np)); CK(ctx->d_pt_b.ensure(sizeof(double) * 3 * (size_t)Np));
-    CK(ctx->d_hidx.ensure(sizeof(int) * (size_t)Nt));
     CK(ctx->d_cams.ensure(sizeof(bagpu_camera) * (size_t)p->n_cameras));
     CK(ctx->d_rigs.ensure(sizeof(double) * 7 * (size_t)std::max(1, p->n_rigs)));
     CK(ctx->d_lm_ptr.ensure(sizeof(int) * ((size_t)Np + 1)));
@@ -692,39 +779,19 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (p->n_rigs) CK(cudaMemcpyAsync(ctx->d_rigs.p, hr, sizeof(double) * 7 * (size_t)p->n_rigs, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_pt_a.p, p->points, sizeof(double) * 3 * (size_t)Np, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_pt_b.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));   // landmarks without observations are never rewritten
-    CK(cudaMemcpyAsync(ctx->d_hidx.p, ctx->h_hidx.data(), sizeof(int) * (size_t)Nt, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_cams.p, p->cameras, sizeof(bagpu_camera) * (size_t)p->n_cameras, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_lm_ptr.p, lm_ptr.data(), sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, st));
+    CK(ctx->h_lmptr.ensure(sizeof(int) * ((size_t)Np + 1)));                     // page-locked copy: a pageable source would make this call wait for the stream
+    memcpy(ctx->h_lmptr.p, lm_ptr.data(), sizeof(int) * ((size_t)Np + 1));
+    // on the plan stream: the tile plan needs it, and on the main stream it would queue behind the bulk of the observation data
+    CK(cudaMemcpyAsync(ctx->d_lm_ptr.p, ctx->h_lmptr.p, sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, sp));
     h2d += sizeof(double) * (7 * (int64_t)Nt + 3 * (int64_t)Np) + sizeof(int) * ((int64_t)Nt + Np + 1);
 
     lap("poses");
-    // --- observations: raw arrays go up as they are; permutation and meta packing happen on the device
-    const size_t ne = (size_t)Ne;
-    CK(ctx->d_o_pose.ensure(4 * ne)); CK(ctx->d_o_point.ensure(4 * ne)); CK(ctx->d_o_meta.ensure(4 * ne));
-    CK(ctx->d_o_u.ensure(8 * ne)); CK(ctx->d_o_v.ensure(8 * ne)); CK(ctx->d_o_w.ensure(8 * ne)); CK(ctx->d_o_ur.ensure(8 * ne));
-    CK(ctx->d_raw8a.ensure(ne)); CK(ctx->d_raw8b.ensure(ne)); CK(ctx->d_raw16a.ensure(2 * ne)); CK(ctx->d_raw16b.ensure(2 * ne));
-    CK(ctx->d_chi2.ensure(8 * ne)); CK(ctx->d_depth.ensure(ne));
-    CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * ne, st));
+    // --- observations (uploaded above): meta packing on the device; another order than landmark-major: permutation + gathers
     const int g = grid_for(Ne, 256);
-    // The index arrays go up first: the pair plan (device, stream sp) needs only them and runs while the bulk of the
-    // observation data is still crossing PCIe on the main stream.
-    cudaStream_t sp = ctx->stream_chol;
-    if (sorted) {
-        CK(cudaMemcpyAsync(ctx->d_o_pose.p, p->obs_pose, 4 * ne, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_o_point.p, p->obs_point, 4 * ne, cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
-    }
-    CK(cudaMemcpyAsync(ctx->d_raw8a.p, p->obs_kind, ne, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_raw8b.p, p->obs_flags, ne, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_raw16a.p, p->obs_cam, 2 * ne, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_raw16b.p, p->obs_rig, 2 * ne, cudaMemcpyHostToDevice, st));
     h2d += 6 * Ne;
     if (sorted) {
-        CK(cudaMemcpyAsync(ctx->d_o_u.p, p->obs_u, 8 * ne, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_o_v.p, p->obs_v, 8 * ne, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_o_w.p, p->obs_inv_sigma2, 8 * ne, cudaMemcpyHostToDevice, st));
-        if (p->obs_ur) CK(cudaMemcpyAsync(ctx->d_o_ur.p, p->obs_ur, 8 * ne, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
         compose_meta_kernel<<<g, 256, 0, st>>>(Ne, ctx->d_raw8a.as<uint8_t>(), ctx->d_raw16a.as<int16_t>(), ctx->d_raw16b.as<int16_t>(),
                                                ctx->d_raw8b.as<uint8_t>(), ctx->d_o_meta.as<uint32_t>());
     } else {
@@ -745,6 +812,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
             if (c.w == 4) gather_perm_kernel<int><<<g, 256, 0, st>>>(Ne, ctx->d_perm.as<int>(), ctx->d_rawd.as<int>(), (int *)c.dst);
             else gather_perm_kernel<double><<<g, 256, 0, st>>>(Ne, ctx->d_perm.as<int>(), ctx->d_rawd.as<double>(), (double *)c.dst);
         }
+        h2d += (4 + 4 + 8 + 8 + 8 + (p->obs_ur ? 8 : 0)) * Ne;      // uploaded twice
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
     }
@@ -755,7 +823,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     CK(cudaMemcpyAsync(ctx->d_pt_init.p, ctx->d_pt_a.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_meta_init.p, ctx->d_o_meta.p, 4 * ne, cudaMemcpyDeviceToDevice, st));
 
-    lap("obs-enqueue");
+    lap("meta");
     const double tw1 = wall();
     // --- reduced camera system: envelope of Hschur from the landmark structure, band or dense storage
     const int n = 6 * nf;
@@ -763,34 +831,50 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     {
         std::vector<int> lastrow(std::max(1, nf));
         for (int h = 0; h < nf; h++) lastrow[h] = h;
-        {
+        CK(cudaEventSynchronize(ctx->ev_lastrow));            // lastrow_kernel on the plan stream (all-reduced over the ranks there)
+        bool any_unsorted = !sorted;
+        if (ctx->world > 1) {
+            // the ranks must take the same path below (it holds a collective): agree on whether any shard came in another order
+            CK(ctx->d_count.ensure(sizeof(unsigned long long) * 2));
+            int *flag = reinterpret_cast<int *>(ctx->d_count.as<unsigned long long>() + 1);
+            int hf = sorted ? 0 : 1;
+            CK(cudaMemcpyAsync(flag, &hf, sizeof(int), cudaMemcpyHostToDevice, sp));
+            CKN(g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, ctx->comm, sp));
+            CK(cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, sp));
+            CK(cudaStreamSynchronize(sp));
+            any_unsorted = hf != 0;
+        }
+        if (sorted) {                                          // computed on the device while the host ran its passes
+            const int *dl = ctx->h_lastrow.as<int>();
+            for (int h = 0; h < nf; h++) lastrow[h] = std::max(lastrow[h], dl[h]);
+        }
+        if (any_unsorted) {
+            // (a shard in another order: its speculative device result is meaningless -- at worst it widens the envelope, which stays valid;
+            // its own rows come from the host pass below, and one more collective gives every rank the union)
+            if (!sorted) {
             std::vector<std::vector<int>> part(kPlanThreads);
             parallel_ranges(Np, 1 << 12, [&](int t, int64_t j0, int64_t j1) {
                 std::vector<int> &lr = part[t];
                 lr.assign(std::max(1, nf), -1);
                 for (int64_t j = j0; j < j1; j++) {
                     int mx = -1;
-                    for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                        const int e = sorted ? a : perm[a];
-                        mx = std::max(mx, ctx->h_hidx[p->obs_pose[e]]);
-                    }
+                    for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) mx = std::max(mx, ctx->h_hidx[p->obs_pose[perm[a]]]);
                     if (mx < 0) continue;
                     for (int a = lm_ptr[j]; a < lm_ptr[j + 1]; a++) {
-                        const int e = sorted ? a : perm[a];
-                        const int h = ctx->h_hidx[p->obs_pose[e]];
+                        const int h = ctx->h_hidx[p->obs_pose[perm[a]]];
                         if (h >= 0) lr[h] = std::max(lr[h], mx);
                     }
                 }
             });
             for (auto &lr : part) for (size_t h = 0; h < lr.size() && (int)h < nf; h++) lastrow[h] = std::max(lastrow[h], lr[h]);
-        }
-        if (ctx->world > 1 && nf > 0) {
-            // every rank must lay the reduced camera system out identically: the envelope is the union over the shards
-            CK(ctx->d_colend.ensure(sizeof(int) * (size_t)nf));
-            CK(cudaMemcpyAsync(ctx->d_colend.p, lastrow.data(), sizeof(int) * (size_t)nf, cudaMemcpyHostToDevice, st));
-            CKN(g_nccl.AllReduce(ctx->d_colend.p, ctx->d_colend.p, (size_t)nf, ncclInt32, ncclMax, ctx->comm, st));
-            CK(cudaMemcpyAsync(lastrow.data(), ctx->d_colend.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            }
+            if (ctx->world > 1 && nf > 0) {
+                CK(ctx->d_colend.ensure(sizeof(int) * (size_t)nf));
+                CK(cudaMemcpyAsync(ctx->d_colend.p, lastrow.data(), sizeof(int) * (size_t)nf, cudaMemcpyHostToDevice, st));
+                CKN(g_nccl.AllReduce(ctx->d_colend.p, ctx->d_colend.p, (size_t)nf, ncclInt32, ncclMax, ctx->comm, st));
+                CK(cudaMemcpyAsync(lastrow.data(), ctx->d_colend.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
         }
         lap("lastrow");
         int bwb = 0;
@@ -1109,6 +1193,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
     if (dbg_t) fprintf(stderr, "[bagpu] upload laps:%s\n", laps.c_str());
     if (dbg_t) fprintf(stderr, "[bagpu] upload host ms: order+copies %.2f envelope %.2f plan %.2f tail+sync %.2f | stream %.2f\n", tw1 - tw0, tw2 - tw1, tw3 - tw2, wall() - tw3, ms);
     ctx->have_problem = true;
+    drain.armed = false;                                   // the stream was synchronised above
     return BAGPU_OK;
 }
 
