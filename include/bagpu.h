@@ -237,6 +237,12 @@ int  bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p);
 int  bagpu_solve_resident(bagpu_ctx *ctx, const bagpu_schedule *s, bagpu_result *r /* may be NULL: no D2H */);
 int  bagpu_download(bagpu_ctx *ctx, bagpu_result *r);
 int  bagpu_reset_resident(bagpu_ctx *ctx);   /* estimates, edge levels and kernels back to the uploaded state */
+/* New estimates for the resident map (same poses / points / observations, same fixed set): pose_qt [n_poses][7], points [n_points][3],
+ * either may be NULL (kept). They become the "uploaded state" of bagpu_reset_resident. The plan of the upload (tile records, envelope,
+ * solver fronts) is kept: a caller that re-optimises one window -- GlobalBundleAdjustemnt re-run after a loop correction moved the
+ * keyframes (src/LoopClosing.cc:2289 after :2330-2460), or local BA twice on one window -- skips the observation upload and the
+ * re-planning (first step: estimates only; adding / removing observations still takes a bagpu_upload). */
+int  bagpu_update_estimates(bagpu_ctx *ctx, const double *pose_qt, const double *points);
 
 int  bagpu_pose_opt_batch(bagpu_ctx *ctx, const bagpu_pose_batch *b, bagpu_pose_result *r);
 /* Split form of the above for device-resident timing. */

@@ -28,7 +28,7 @@ _LIB = None
 
 EXPORTS = ["bagpu_init", "bagpu_destroy", "bagpu_strerror", "bagpu_last_error", "bagpu_comm_unique_id",
            "bagpu_comm_init", "bagpu_pin_host", "bagpu_unpin_host", "bagpu_solve_ba", "bagpu_upload",
-           "bagpu_solve_resident", "bagpu_download", "bagpu_reset_resident", "bagpu_pose_opt_batch", "bagpu_pose_upload",
+           "bagpu_solve_resident", "bagpu_download", "bagpu_reset_resident", "bagpu_update_estimates", "bagpu_pose_opt_batch", "bagpu_pose_upload",
            "bagpu_pose_solve_resident", "bagpu_get_timing", "bagpu_test_atan2f", "bagpu_test_solve", "bagpu_test_solve_parts", "bagpu_test_fp64_peak"]
 
 
@@ -64,6 +64,7 @@ def load_library():
     L.bagpu_solve_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bagpu_download.argtypes = [C.c_void_p, C.c_void_p]
     L.bagpu_reset_resident.argtypes = [C.c_void_p]
+    L.bagpu_update_estimates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bagpu_pose_opt_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bagpu_pose_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.bagpu_pose_solve_resident.argtypes = [C.c_void_p, C.c_void_p]
@@ -162,6 +163,12 @@ class Context:
 
     def reset_resident(self):
         self._check(self.lib.bagpu_reset_resident(self.h))
+
+    def update_estimates(self, pose_qt=None, points=None):
+        """New estimates for the resident map (same structure): the upload's plan is kept (bagpu_update_estimates)."""
+        pq = None if pose_qt is None else np.ascontiguousarray(pose_qt, np.float64)
+        pt = None if points is None else np.ascontiguousarray(points, np.float64)
+        self._check(self.lib.bagpu_update_estimates(self.h, None if pq is None else pq.ctypes.data, None if pt is None else pt.ctypes.data))
 
     # -- PoseOptimization
     def pose_opt_batch(self, batch: PoseBatch) -> PoseResult:

@@ -389,14 +389,20 @@ __global__ void atan2f_test_kernel(int64_t n, const float *y, const float *x, fl
 
 // envelope of the reduced system from the landmark structure: lastrow[h] = largest free index among the poses that share a landmark with
 // free pose h (observations landmark-major, pose-ascending: the partner with the largest index is the last free observation of the run)
-__global__ void lastrow_kernel(int64_t n_obs, const int *__restrict__ o_pose, const int *__restrict__ o_point, const int *__restrict__ hidx, int *lastrow) {
+__global__ void lastrow_kernel(int64_t n_obs, int n_poses, const int *__restrict__ o_pose, const int *__restrict__ o_point, const int *__restrict__ hidx, int *lastrow) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_obs) return;
-    const int h = hidx[o_pose[e]];
+    // (runs on the arrays as uploaded, BEFORE the host has validated them: an index out of range is skipped here and reported there)
+    const int ip = o_pose[e];
+    if ((unsigned)ip >= (unsigned)n_poses) return;
+    const int h = hidx[ip];
     if (h < 0) return;
     const int j = o_point[e];
     int mx = h;
-    for (int64_t e2 = e + 1; e2 < n_obs && o_point[e2] == j; e2++) mx = max(mx, hidx[o_pose[e2]]);
+    for (int64_t e2 = e + 1; e2 < n_obs && o_point[e2] == j; e2++) {
+        const int i2 = o_pose[e2];
+        if ((unsigned)i2 < (unsigned)n_poses) mx = max(mx, hidx[i2]);
+    }
     atomicMax(lastrow + h, mx);
 }
 
@@ -674,7 +680,7 @@ int bagpu_upload(bagpu_ctx *ctx, const bagpu_problem *p) {
         CK(ctx->d_lastrow.ensure(sizeof(int) * (size_t)std::max(1, nf))); CK(ctx->h_lastrow.ensure(sizeof(int) * (size_t)std::max(1, nf)));
         CK(cudaStreamWaitEvent(sp, ctx->ev_fork, 0));
         CK(cudaMemsetAsync(ctx->d_lastrow.p, 0xff, sizeof(int) * (size_t)std::max(1, nf), sp));
-        lastrow_kernel<<<grid_for(Ne, 256), 256, 0, sp>>>(Ne, ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(), ctx->d_lastrow.as<int>());
+        lastrow_kernel<<<grid_for(Ne, 256), 256, 0, sp>>>(Ne, Nt, ctx->d_o_pose.as<int>(), ctx->d_o_point.as<int>(), ctx->d_hidx.as<int>(), ctx->d_lastrow.as<int>());
         // every rank must lay the reduced camera system out identically: the envelope is the union over the shards
         if (ctx->world > 1 && nf > 0) CKN(g_nccl.AllReduce(ctx->d_lastrow.p, ctx->d_lastrow.p, (size_t)nf, ncclInt32, ncclMax, ctx->comm, sp));
         CK(cudaMemcpyAsync(ctx->h_lastrow.p, ctx->d_lastrow.p, sizeof(int) * (size_t)std::max(1, nf), cudaMemcpyDeviceToHost, sp));
@@ -2150,6 +2156,23 @@ int bagpu_reset_resident(bagpu_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->d_chi2.p, 0, 8 * (size_t)ctx->n_obs, st));
     CK(cudaStreamSynchronize(st));
     return BAGPU_OK;
+}
+
+int bagpu_update_estimates(bagpu_ctx *ctx, const double *pose_qt, const double *points) {
+    if (!ctx) return BAGPU_ERR_ARG;
+    if (!ctx->have_problem) return fail(ctx, BAGPU_ERR_ARG, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t pb = sizeof(double) * 7 * (size_t)ctx->n_poses, qb = sizeof(double) * 3 * (size_t)ctx->n_points;
+    if (pose_qt) {
+        CK(ctx->h_stage.ensure(pb));
+        double *hp = ctx->h_stage.as<double>();
+        for (int i = 0; i < ctx->n_poses; i++) normalize_qt(pose_qt + 7 * (size_t)i, hp + 7 * (size_t)i);
+        CK(cudaMemcpyAsync(ctx->d_pose_init.p, hp, pb, cudaMemcpyHostToDevice, st));
+    }
+    if (points) CK(cudaMemcpyAsync(ctx->d_pt_init.p, points, qb, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                           // the caller's arrays (and h_stage) may be reused on return
+    return bagpu_reset_resident(ctx);                        // both state buffers, edge levels and kernels from the (new) uploaded state
 }
 
 int bagpu_download(bagpu_ctx *ctx, bagpu_result *r) {

@@ -73,6 +73,33 @@ def test_stop_flag_written_by_another_thread_mid_solve(ctx):
         assert a["trials"] == b["trials"] and abs(a["chi2_after"] - b["chi2_after"]) <= 1e-12 * b["chi2_after"]
 
 
+def test_update_estimates_keeps_the_plan(ctx):
+    """bagpu_update_estimates: new poses / points for the resident map (first step). Re-optimising the same window from
+    other estimates through the kept plan gives bit for bit what a fresh bagpu_solve_ba of that problem gives, and a reset goes back to
+    the NEW uploaded state."""
+    p = synthetic.config(2, scale=0.3)
+    rng = np.random.default_rng(11)
+    pose2 = p.pose_qt.copy(); pose2[:, :3] += rng.normal(0, 0.01, (p.n_poses, 3))
+    pts2 = p.points + rng.normal(0, 0.02, p.points.shape)
+    q = problem.BAProblem(pose2, p.pose_fixed, pts2, p.cameras, p.rigs, p.obs_pose, p.obs_point, p.obs_cam, p.obs_rig, p.obs_kind,
+                          p.obs_flags, p.obs_u, p.obs_v, p.obs_ur, p.obs_inv_sigma2)
+    s = problem.schedule_merge_ba()
+    fresh = ctx.solve_ba(q, s)
+    ctx.upload(p)
+    ctx.solve_resident(s, download=False)                       # the map has been optimised (and its edge levels changed) before the update
+    ctx.update_estimates(pose2, pts2)
+    kept = ctx.solve_resident(s)
+    assert [t["trials"] for t in kept.trace] == [t["trials"] for t in fresh.trace]
+    assert np.array_equal(kept.pose_qt, fresh.pose_qt) and np.array_equal(kept.points, fresh.points)
+    assert np.array_equal(kept.edge_level, fresh.edge_level)
+    ctx.reset_resident()
+    again = ctx.solve_resident(s)
+    assert np.array_equal(again.pose_qt, fresh.pose_qt)
+    ctx.update_estimates(points=p.points)                       # points only: poses stay the updated ones
+    mixed = ctx.solve_resident(s)
+    assert np.isfinite(mixed.pose_qt).all() and not np.array_equal(mixed.points, fresh.points)
+
+
 def test_per_iteration_phase_record(ctx):
     """bagpu_trace carries the G2OBatchStatistics view (Thirdparty/g2o/g2o/core/batch_stats.h:40-62): edges and per-phase times."""
     p = synthetic.config(2)
