@@ -9,7 +9,7 @@ print(f"poses {p.n_poses} points {p.n_points} obs {p.n_obs}", flush=True)
 s = problem.schedule_global_ba(20)
 base = None
 NO = {"BAGPU_NO_OVERLAP": "1"}
-for parts, extra in [("2", {}), ("2", NO), ("8", dict(NO, BAGPU_SEP_TILED="1")), ("8", NO), ("12", NO), ("16", NO), ("20", NO), ("24", NO), ("32", NO), ("16", {})]:
+for parts, extra in [("12", NO), ("13", NO), ("14", NO), ("15", NO), ("16", NO), ("10", NO)]:
     os.environ["BAGPU_PARTS"] = parts
     for k in ("BAGPU_NO_OVERLAP", "BAGPU_SEP_TILED"):
         os.environ.pop(k, None)
