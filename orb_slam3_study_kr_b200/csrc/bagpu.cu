@@ -1335,21 +1335,12 @@ int parts_plan(bagpu_ctx *ctx, PartPlan &pp, int n, int ld, const std::vector<in
         // ~16 us per panel). More than ~100 SMs of spinning clusters slow each other down through L2 (16 fronts: 3.7 ms, 12: 2.8 ms).
         const double panels = n / 32.0, two_way = panels / 2 * 16.0 + 250.0;
         double best = 0.8 * two_way;
-        // as many fronts as clusters can be co-resident (one more would run as a second wave behind the others: measured on config 5,
-        // 12 / 13 / 14 fronts: 2.54 / 2.42 / 2.78 ms per solve): ask the occupancy calculator, the clusters must fit the GPCs
+        // Fronts: measured on config 5 (B200, clusters of 8 CTAs), 10 / 12 / 13 / 14 / 15 / 16 fronts: 2.98 / 2.54 / 2.42 / 2.78 / 3.14 / 3.48 ms
+        // per solve. Beyond 13 clusters (104 of 148 SMs) the fronts slow each other down although cudaOccupancyMaxActiveClusters reports
+        // 15 or more co-resident (an 8-GPU run with 15 fronts: 3.12 ms): the bound is the measured 70 % of the SMs, not the calculator's.
         int nc_guess = 2;
         while (nc_guess * CH_NB < std::min(CB_MAXR, band_rows + CH_NB)) nc_guess *= 2;
-        int max_fronts = (2 * ctx->n_sm) / (3 * nc_guess);
-        {
-            cudaLaunchConfig_t cfg = {};
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = nc_guess; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.gridDim = dim3(nc_guess * PS_MAX_PARTS); cfg.blockDim = dim3(CB_THREADS); cfg.attrs = at; cfg.numAttrs = 1;
-            cfg.dynamicSmemBytes = chol_band_smem(ctx, std::min(n, 4096), std::min(CB_MAXR, band_rows + CH_NB));
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, chol_band_kernel, &cfg) == cudaSuccess && ncl > 0) max_fronts = ncl; else cudaGetLastError();
-        }
+        const int max_fronts = std::max(3, (45 * ctx->n_sm) / (64 * nc_guess));
         for (int q = 3; q <= PS_MAX_PARTS && q <= max_fronts; q++) {
             const int per = interior_of(q);
             if (per < std::max(2 * w, 576)) break;
