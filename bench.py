@@ -22,7 +22,7 @@ carries both strong-scaling curves. A step = one Optimizer::GlobalBundleAdjustem
           library's stream) against the measured HBM copy bandwidth; roofline_fp64 reports the same pass against the FP64
           throughput measured on the device (the Schur products are FP64 work; they run on the FP64 tensor pipe,
           mma.sync.m8n8k4.f64). On config 4 (one GPU) the two-front band Cholesky runs BESIDE the pass on a second stream, so the
-          `kernels` shares overlap and sum to more than 1; on config 5 the twelve-front solver runs after it.
+          `kernels` shares overlap and sum to more than 1; on config 5 the 13-front solver runs after it.
   parity_check  before the timed region every run solves a small map (config 4 at 1/10 size, merge schedule: two rounds and
           a gate) sharded over the N ranks and compares rank 0's result with the CPU oracle (1e-6 on chi2 per iteration
           and on the estimates, identical trial counts and edge levels): the multi-GPU path is checked where it is timed.
