@@ -29,6 +29,7 @@
 #include "schur_tiles.cuh"
 #include "chol.cuh"
 #include "chol_parts.cuh"
+#include "chol_small.cuh"
 #include "pcg.cuh"
 #include "pose_opt.cuh"
 
@@ -123,6 +124,8 @@ struct BagpuOptions {
     bool no_back3 = false;       // BAGPU_NO_BACK3: two-buffer backward substitution
     int  parts = 0;              // BAGPU_PARTS: number of partitions of the partitioned band solver (0 = automatic, 1 = off)
     bool sep_tiled = false;      // BAGPU_SEP_TILED: separator system through the tiled band solver instead of block cyclic reduction
+    bool small_chol = false;     // BAGPU_SMALL_CHOL: chained loop solves systems of n <= 224 through chol_small_kernel (one CTA, one barrier per column;
+                                 // measured slower than the cluster kernel: 130 against 62 us for n = 120, 268 against 90 us for n = 180 -- off)
     bool no_chain = false;       // BAGPU_NO_CHAIN: host-stepped LM loop (one status read per trial) even for small maps
     long long chain_obs = 600000; // BAGPU_CHAIN_OBS: largest map (observations) whose LM loop runs chained on the device
     bool tile_fma = false;       // BAGPU_TILE_FMA: the tile contraction with FMAs in registers (pair_tile_kernel) instead of the FP64 tensor pipe (pair_tile_mma_kernel)
@@ -140,7 +143,7 @@ struct BagpuOptions {
         if (getenv("BAGPU_STAGE_FIRST")) stage_first = atoi(getenv("BAGPU_STAGE_FIRST"));
         update_relin = on("BAGPU_UPDATE_RELIN"); no_band = on("BAGPU_NO_BAND"); no_cluster = on("BAGPU_NO_CLUSTER"); no_back3 = on("BAGPU_NO_BACK3");
         if (getenv("BAGPU_PARTS")) parts = atoi(getenv("BAGPU_PARTS"));
-        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); spike_v1 = on("BAGPU_SPIKE_V1"); chunks = on("BAGPU_CHUNKS"); tile_fma = on("BAGPU_TILE_FMA"); no_chain = on("BAGPU_NO_CHAIN");
+        sep_tiled = on("BAGPU_SEP_TILED"); pair_list = on("BAGPU_PAIR_LIST"); spike_v1 = on("BAGPU_SPIKE_V1"); chunks = on("BAGPU_CHUNKS"); tile_fma = on("BAGPU_TILE_FMA"); no_chain = on("BAGPU_NO_CHAIN"); small_chol = on("BAGPU_SMALL_CHOL");
         if (getenv("BAGPU_CHAIN_OBS")) chain_obs = atoll(getenv("BAGPU_CHAIN_OBS"));
     }
 };
@@ -544,7 +547,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
                              (const void *)panel_inverse_kernel, (const void *)spike_forward_kernel, (const void *)spike_forward2_kernel, (const void *)spike_gram_kernel, (const void *)sep_assemble_kernel,
                              (const void *)sep_scatter_kernel, (const void *)spike_apply_kernel, (const void *)row_order_parts_kernel,
                              (const void *)pcg_prec_kernel, (const void *)pcg_init_kernel, (const void *)pcg_init_finish_kernel, (const void *)pcg_spmv_kernel, (const void *)pcg_update_kernel, (const void *)pcg_dir_kernel,
-                             (const void *)lm_init_kernel, (const void *)lm_decide_kernel, (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
+                             (const void *)chol_small_kernel, (const void *)lm_init_kernel, (const void *)lm_decide_kernel, (const void *)pair_tile_kernel, (const void *)pair_tile_mma_kernel, (const void *)tile_diag_kernel, (const void *)tile_order_kernel, (const void *)tile_plan_kernel<false>, (const void *)tile_plan_kernel<true>, (const void *)tile_gather_kernel,
                              (const void *)tile_item_count_kernel, (const void *)tile_item_fill_kernel, (const void *)cr_assemble_kernel, (const void *)block_inverse_kernel, (const void *)block_spike_kernel, (const void *)block_gram_kernel, (const void *)block_apply_kernel};
         for (const void *f : fns) if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) { cudaGetLastError(); }
         // Function attributes are PER DEVICE: every context sets them for its own device (idempotent, no process-wide flag),
@@ -559,6 +562,7 @@ int bagpu_init(int device_id, bagpu_ctx **out) {
         ok_attr &= cudaFuncSetAttribute(chol_solve_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem_cap) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok_attr &= cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_small_smem(CS_MAX_N)) == cudaSuccess;
         ok_attr &= cudaFuncSetAttribute(spike_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem_cap) == cudaSuccess;
         if (!ok_attr) { cudaGetLastError(); bagpu_destroy(ctx); return BAGPU_ERR_CUDA; }
     }
@@ -1685,7 +1689,9 @@ int optimize_chained(bagpu_ctx *ctx, const bagpu_schedule *s, int round, int ite
         cudaEventRecord(T.e[1], st);
         CholArgs ca; ca.S = L.S; ca.n = n; ca.ld = ctx->ld; ca.lambda = 0.0; ca.bp = L.bp; ca.bs = L.bs; ca.prof = nullptr; ca.x = ctx->d_xp.as<double>(); ca.y = L.y1;
         ca.dinv = ctx->d_dinv.as<double>(); ca.col_end = ctx->d_colend.as<int>(); ca.fail = L.fail; ca.lm = lm;
-        { int rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, st); if (rc) return rc; }
+        if (n <= CS_MAX_N && ctx->opt.small_chol)               // opt-in: one CTA, packed in shared memory, one barrier per column (measured slower)
+            chol_small_kernel<<<1, CS_THREADS, chol_small_smem(n), st>>>(L.S, n, ctx->ld, 0.0, L.bp, L.bs, ctx->d_xp.as<double>(), L.fail, lm);
+        else { int rc = launch_chol(ctx, ca, ctx->chol_grid, ctx->chol_maxr, st); if (rc) return rc; }
         cudaEventRecord(T.e[2], st);
         pose_update_kernel<<<1, 256, 0, st>>>(ctx->n_poses, ctx->d_hidx.as<int>(), pose_a, pose_b, ctx->d_xp.as<double>(), L.bp, 0.0, dstat + 4, lm);
         UpdateOut U; U.lambda = 0.0; U.xp = ctx->d_xp.as<double>(); U.pose_trial = pose_b; U.pt_trial = pt_b;
