@@ -374,9 +374,12 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     achieved = alg_bytes / (build_avg_ms * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "build_pass_traffic.json")
+    tensor_pct = None
     if os.path.exists(tf) and world == 1:
         try:
-            traffic = json.load(open(tf)).get(which, {}).get("dram_bytes_per_launch")     # ncu --set full capture of the same workload
+            prof = json.load(open(tf)).get(which, {})                                     # ncu --set full capture of the same workload
+            traffic = prof.get("dram_bytes_per_launch")
+            tensor_pct = prof.get("pair_tile_mma_kernel", {}).get("dmma_pipe_active_pct")
         except Exception:
             traffic = None
     fp64 = ctx.fp64_peak()
@@ -419,6 +422,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                                   "frac": alg_flops / (build_avg_ms * 1e-3) / 1e12 / max(fp64["dfma_tflops"], 1e-9),
                                   "algorithmic_flops_per_launch": alg_flops, "peak_source": "measured on this device by bagpu_test_fp64_peak (DFMA probe)",
                                   "dmma_peak_tflops": fp64["dmma_tflops"],
+                                  "tensor_pipe_active_pct_ncu": tensor_pct,      # pair_tile_mma_kernel, FP64 tensor pipe (profiles/r02g_full_raw_*.csv); not measured live
                                   "bound_time_ms": {"hbm": alg_bytes / (peak * 1e9) * 1e3, "fp64": alg_flops / (fp64["dfma_tflops"] * 1e12) * 1e3}},
                 "kernels": {"build_ms_per_step": acc["build_ms"] / steps, "linsolve_ms_per_step": acc["linsolve_ms"] / steps,
                             "update_ms_per_step": acc["update_ms"] / steps,
