@@ -24,6 +24,9 @@
 #define DR_STRIDE 16                       // 15 used: [w M^T M (6) | M^T g (3) | Y L^-1 b_l (3) | X_l (3)]: 128 bytes = exactly two 64-byte L2 fetches per gather
                                            // (a 96-byte record + the X_l sector of the Z record costs 128 + 64 bytes of DRAM reads at the L2's 64-byte fetch granularity)
 #define LM_STRIDE 12
+#ifndef UZ_MINB
+#define UZ_MINB 3                          // resident CTAs per SM asked of the compiler for update_z_kernel
+#endif
 #ifndef PK_CHUNK
 #define PK_CHUNK 512                       // entries per work item (per-item reductions vs the working set of the chunks in flight)
 #endif
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MINB) pair_kernel(PairArgs P) {
 // x_l = L^-T (L^-1 b_l - sum_obs Z^T x_p): one 160-byte record and 18 FMA per observation, three sums per landmark. Then the
 // same evaluation of every edge at the trial state as update_packed_kernel (computeActiveErrors + activeRobustChi2) and the
 // landmark part of computeScale.
-__global__ void __launch_bounds__(ST_THREADS, 3) update_z_kernel(BaDev D, const double *__restrict__ pt_in, UpdateOut O, UpdateTasks K,
+__global__ void __launch_bounds__(ST_THREADS, UZ_MINB) update_z_kernel(BaDev D, const double *__restrict__ pt_in, UpdateOut O, UpdateTasks K,
                                                                  const double *__restrict__ Zr, const double *__restrict__ Lm) {
     __shared__ double s_chi[ST_WARPS], s_sc[ST_WARPS];
     const double *pt = pt_in, *pose_unused = nullptr;
