@@ -117,7 +117,8 @@ typedef struct bagpu_schedule {
     double  delta_mono;             /* Huber delta as the reference stores it: (double)(float)sqrt(5.991) etc. */
     double  delta_stereo;
     double  lambda_init;            /* <=0: tau*max diag (tau=1e-5); >0: setUserLambdaInit  (Optimizer.cc:1197-1198) */
-    const volatile uint8_t *stop_flag; /* the caller's bool* pbStopFlag, may be NULL; polled where g2o polls terminate() */
+    const volatile uint8_t *stop_flag; /* the caller's bool* pbStopFlag, may be NULL; polled where g2o polls terminate() (small maps run the LM
+                                        * loop chained on the device and poll it every four trials) */
     int32_t linear_solver;          /* BAGPU_SOLVER_* */
     int32_t max_trace;              /* capacity of bagpu_result.trace (entries)            */
     double  pcg_tolerance;          /* BAGPU_SOLVER_PCG: stop at |r| <= tol |b| (<= 0: 1e-10) */
@@ -146,8 +147,8 @@ typedef struct bagpu_trace {
     /* per-iteration phase record (G2OBatchStatistics: numEdges, timeLinearize + timeQuadraticForm + timeSchurComplement,
      * timeLinearSolver, timeUpdate + timeResiduals, timeIteration); device times from CUDA events, summed over the trials */
     int64_t active_edges;           /* numEdges: level-0 edges of this round                */
-    double  linearise_schur_us;     /* stage_kernel + pair_kernel (all trials of the iteration) */
-    double  linear_solve_us;        /* reduced camera system; on one GPU it runs BESIDE pair_kernel, so the phases overlap */
+    double  linearise_schur_us;     /* stage_kernel + tile_diag_kernel + pair_tile_mma_kernel (all trials of the iteration) */
+    double  linear_solve_us;        /* reduced camera system; the two-front solver of a mid-sized map runs BESIDE the pass, so the phases overlap there */
     double  update_us;              /* back-substitution, update, evaluation                 */
     double  iteration_us;           /* host wall clock of the whole iteration                */
 } bagpu_trace;
